@@ -1,0 +1,450 @@
+// C ABI of libravvent_b200.so: model handle, weight packing, and the drivers that chain
+// K2/K3/K4/K5 into Basecaller._encode_input / greedy_search_prediction /
+// beam_search_prediction (reference basecaller.py:296-330, 395-416).
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace rvb {
+std::atomic<long long> g_launches{0};
+
+// utils.input_mask (utils.py:26-32): mask[b,t] = all_f(x[b,t,f] != 0)
+__global__ void input_mask_kernel(const float *x, int F, long long B, int T, uint8_t *mask, int Tm, int t_off) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    long long b = i / T; int t = (int)(i % T);
+    bool ok = true;
+    for (int f = 0; f < F; ++f) ok = ok && (x[i * F + f] != 0.0f);
+    mask[b * Tm + t_off + t] = ok ? 1 : 0;
+}
+}  // namespace rvb
+
+using namespace rvb;
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct rvb_model {
+    int device = 0, enc_depth = 2, dec_depth = 1, input_kind = RVB_INPUT_JOINT, precision = RVB_PREC_FP32;
+    int wave = 9472;
+    bool finalized = false;
+    bool use_tc = false;
+    std::map<std::string, HostTensor> hw;
+    // packed device weights
+    float *d_rec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float *d_pw[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float *d_pb[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float *d_wmem = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
+    // workspace for one wave
+    size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
+    float *y_raw[2] = {nullptr, nullptr}, *y_ev[2] = {nullptr, nullptr};
+    float *G_raw = nullptr, *G_ev = nullptr;
+    float *st[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [encoder][ping-pong]
+    float *enc_out = nullptr, *keys = nullptr;
+    uint8_t *mask = nullptr;
+    int32_t *step_ids = nullptr, *parent_ids = nullptr;
+    // host-variant device buffers
+    size_t hb_cap = 0;
+    float *hb_raw = nullptr, *hb_ev = nullptr, *hb_scores = nullptr;
+    int32_t *hb_ids = nullptr, *hb_steps = nullptr;
+    cudaStream_t hstream = nullptr;
+    std::vector<void *> owned;
+};
+
+template <typename T>
+static int dmalloc(rvb_model *m, T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(RVB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+    m->owned.push_back(q);
+    *p = reinterpret_cast<T *>(q);
+    return RVB_OK;
+}
+static void dfree(rvb_model *m, void *p) {
+    if (!p) return;
+    for (auto &q : m->owned)
+        if (q == p) { cudaFree(q); q = nullptr; }
+}
+
+extern "C" int rvb_version(void) { return 100; }
+extern "C" const char *rvb_last_error(void) { return err_buf(); }
+extern "C" int64_t rvb_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" int rvb_device_count(int *count) {
+    if (!count) return fail(RVB_ERR_ARG, "null count");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *count = n;
+    return RVB_OK;
+}
+
+extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, int dec_units, int encoder_depth,
+                                int decoder_depth, int vocab_size, int input_kind, int precision, int wave_snippets) {
+    if (!out) return fail(RVB_ERR_ARG, "null out");
+    if (enc_units != UNITS || dec_units != UNITS)
+        return fail(RVB_ERR_ARG, "kernels are specialised for enc_units == dec_units == 128 (got %d, %d)", enc_units, dec_units);
+    if (encoder_depth < 1 || encoder_depth > 3) return fail(RVB_ERR_ARG, "encoder_depth must be 1..3");
+    if (decoder_depth != 1) return fail(RVB_ERR_ARG, "decoder_depth must be 1 in this build");
+    if (vocab_size != VOCAB) return fail(RVB_ERR_ARG, "vocab_size must be 7");
+    if (input_kind < 0 || input_kind > 2) return fail(RVB_ERR_ARG, "bad input_kind");
+    if (precision != RVB_PREC_FP32 && precision != RVB_PREC_BF16) return fail(RVB_ERR_ARG, "bad precision");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(RVB_ERR_CUDA, "no CUDA device: libravvent_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(RVB_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    RVB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RVB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(RVB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    rvb_model *m = new rvb_model();
+    m->device = device; m->enc_depth = encoder_depth; m->dec_depth = decoder_depth;
+    m->input_kind = input_kind; m->precision = precision;
+    if (wave_snippets > 0) m->wave = (wave_snippets + 63) / 64 * 64;
+    const char *g = getenv("RVB_GEMM");
+    m->use_tc = gemm::tc_available() && !(g && strcmp(g, "simt") == 0);
+    *out = m;
+    return RVB_OK;
+}
+
+extern "C" int rvb_model_destroy(rvb_model_t *m) {
+    if (!m) return RVB_OK;
+    cudaSetDevice(m->device);
+    for (void *q : m->owned) if (q) cudaFree(q);
+    if (m->hstream) cudaStreamDestroy(m->hstream);
+    delete m;
+    return RVB_OK;
+}
+
+extern "C" int rvb_model_set_weight(rvb_model_t *m, const char *name, const float *h_data, const int64_t *shape, int ndim) {
+    if (!m || !name || !h_data || !shape || ndim < 1 || ndim > 2) return fail(RVB_ERR_ARG, "set_weight: bad argument");
+    size_t n = 1;
+    HostTensor t;
+    for (int i = 0; i < ndim; ++i) { if (shape[i] <= 0) return fail(RVB_ERR_ARG, "set_weight: bad shape"); n *= (size_t)shape[i]; t.shape.push_back(shape[i]); }
+    t.data.assign(h_data, h_data + n);
+    m->hw[name] = std::move(t);
+    m->finalized = false;
+    return RVB_OK;
+}
+
+static int get_w(rvb_model *m, const std::string &name, int64_t d0, int64_t d1, const HostTensor **out) {
+    auto it = m->hw.find(name);
+    if (it == m->hw.end()) return fail(RVB_ERR_STATE, "missing weight '%s'", name.c_str());
+    const HostTensor &t = it->second;
+    bool ok = d1 < 0 ? (t.shape.size() == 1 && t.shape[0] == d0) : (t.shape.size() == 2 && t.shape[0] == d0 && t.shape[1] == d1);
+    if (!ok) return fail(RVB_ERR_ARG, "weight '%s' has the wrong shape", name.c_str());
+    *out = &t;
+    return RVB_OK;
+}
+
+static int upload(rvb_model *m, float **dst, const std::vector<float> &v) {
+    RVB_CHECK(dmalloc(m, dst, v.size()));
+    RVB_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RVB_OK;
+}
+
+extern "C" int rvb_model_finalize(rvb_model_t *m) {
+    if (!m) return fail(RVB_ERR_ARG, "null model");
+    RVB_CUDA(cudaSetDevice(m->device));
+    const char *enc_name[2] = {"encoder_raw", "encoder_event"};
+    const int enc_feat[2] = {1, 5};
+    const char *dir_name[2] = {"forward", "backward"};
+    for (int e = 0; e < 2; ++e) {
+        if (e == 0 && m->input_kind == RVB_INPUT_EVENT) continue;
+        if (e == 1 && m->input_kind == RVB_INPUT_RAW) continue;
+        for (int l = 0; l < m->enc_depth; ++l) {
+            const int F = l == 0 ? enc_feat[e] : ENC_OUT;
+            const int KX = rec::kx_rows(l == 0 ? enc_feat[e] : 0);
+            std::vector<float> pack((size_t)2 * 2 * KX * 256);
+            std::vector<float> wcat, bcat;
+            if (l > 0) { wcat.resize((size_t)ENC_OUT * 2 * GATES); bcat.resize(2 * GATES); }
+            for (int d = 0; d < 2; ++d) {
+                std::string base = std::string(enc_name[e]) + "/layer" + std::to_string(l) + "/" + dir_name[d] + "/";
+                const HostTensor *W, *U, *Bv;
+                RVB_CHECK(get_w(m, base + "kernel", F, GATES, &W));
+                RVB_CHECK(get_w(m, base + "recurrent_kernel", UNITS, GATES, &U));
+                RVB_CHECK(get_w(m, base + "bias", GATES, -1, &Bv));
+                for (int r = 0; r < 2; ++r)
+                    for (int k = 0; k < KX; ++k)
+                        for (int g = 0; g < 4; ++g)
+                            for (int u = 0; u < 64; ++u) {
+                                const int col = g * UNITS + 64 * r + u;
+                                float v;
+                                if (k < UNITS) v = U->data[(size_t)k * GATES + col];
+                                else if (k < UNITS + F) v = W->data[(size_t)(k - UNITS) * GATES + col];
+                                else v = Bv->data[col];
+                                pack[(((size_t)(d * 2 + r) * KX + k) * 4 + g) * 64 + u] = v;
+                            }
+                if (l > 0) {
+                    for (int k = 0; k < ENC_OUT; ++k)
+                        for (int n = 0; n < GATES; ++n) wcat[(size_t)k * 2 * GATES + d * GATES + n] = W->data[(size_t)k * GATES + n];
+                    for (int n = 0; n < GATES; ++n) bcat[d * GATES + n] = Bv->data[n];
+                }
+            }
+            RVB_CHECK(upload(m, &m->d_rec[e][l], pack));
+            if (l > 0) { RVB_CHECK(upload(m, &m->d_pw[e][l], wcat)); RVB_CHECK(upload(m, &m->d_pb[e][l], bcat)); }
+        }
+    }
+    {
+        const HostTensor *Wd, *Ud, *Bd, *Wm, *Wa, *Wf, *Bf;
+        RVB_CHECK(get_w(m, "decoder/cell0/kernel", VOCAB + UNITS, GATES, &Wd));
+        RVB_CHECK(get_w(m, "decoder/cell0/recurrent_kernel", UNITS, GATES, &Ud));
+        RVB_CHECK(get_w(m, "decoder/cell0/bias", GATES, -1, &Bd));
+        RVB_CHECK(get_w(m, "decoder/memory_layer/kernel", ENC_OUT, UNITS, &Wm));
+        RVB_CHECK(get_w(m, "decoder/attention_layer/kernel", UNITS + ENC_OUT, UNITS, &Wa));
+        RVB_CHECK(get_w(m, "decoder/fc/kernel", UNITS, VOCAB, &Wf));
+        RVB_CHECK(get_w(m, "decoder/fc/bias", VOCAB, -1, &Bf));
+        std::vector<float> wg((size_t)2 * UNITS * UNITS * 4), wtok((size_t)VOCAB * UNITS * 4);
+        for (int k = 0; k < 2 * UNITS; ++k)
+            for (int u = 0; u < UNITS; ++u)
+                for (int g = 0; g < 4; ++g)
+                    wg[((size_t)k * UNITS + u) * 4 + g] = k < UNITS ? Wd->data[(size_t)(VOCAB + k) * GATES + g * UNITS + u]
+                                                                    : Ud->data[(size_t)(k - UNITS) * GATES + g * UNITS + u];
+        for (int v = 0; v < VOCAB; ++v)
+            for (int u = 0; u < UNITS; ++u)
+                for (int g = 0; g < 4; ++g)
+                    wtok[((size_t)v * UNITS + u) * 4 + g] = Wd->data[(size_t)v * GATES + g * UNITS + u] + Bd->data[g * UNITS + u];
+        RVB_CHECK(upload(m, &m->d_wg, wg));
+        RVB_CHECK(upload(m, &m->d_wtok, wtok));
+        RVB_CHECK(upload(m, &m->d_wmem, Wm->data));
+        RVB_CHECK(upload(m, &m->d_watt, Wa->data));
+        RVB_CHECK(upload(m, &m->d_wfc, Wf->data));
+        RVB_CHECK(upload(m, &m->d_bfc, Bf->data));
+    }
+    m->finalized = true;
+    return RVB_OK;
+}
+
+static int project(rvb_model *m, const float *A, const float *W, const float *bias, float *C, long long M, int N, int K,
+                   cudaStream_t s) {
+    if (m->use_tc) return gemm::run_tc(A, W, bias, C, M, N, K, m->precision, s);
+    return gemm::run_simt(A, W, bias, C, M, N, K, s);
+}
+
+static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
+    const size_t wv = (size_t)m->wave;
+    const int Tm = t_raw + t_ev;
+    if ((size_t)t_raw > m->ws_raw_t) {
+        for (int i = 0; i < 2; ++i) { dfree(m, m->y_raw[i]); RVB_CHECK(dmalloc(m, &m->y_raw[i], wv * t_raw * ENC_OUT)); }
+        dfree(m, m->G_raw);
+        if (m->enc_depth > 1) RVB_CHECK(dmalloc(m, &m->G_raw, wv * t_raw * 2 * GATES));
+        m->ws_raw_t = t_raw;
+    }
+    if ((size_t)t_ev > m->ws_ev_t) {
+        for (int i = 0; i < 2; ++i) { dfree(m, m->y_ev[i]); RVB_CHECK(dmalloc(m, &m->y_ev[i], wv * t_ev * ENC_OUT)); }
+        dfree(m, m->G_ev);
+        if (m->enc_depth > 1) RVB_CHECK(dmalloc(m, &m->G_ev, wv * t_ev * 2 * GATES));
+        m->ws_ev_t = t_ev;
+    }
+    if (!m->st[0][0])
+        for (int e = 0; e < 2; ++e)
+            for (int i = 0; i < 2; ++i) RVB_CHECK(dmalloc(m, &m->st[e][i], wv * 2 * 2 * UNITS));
+    if ((size_t)Tm > m->ws_tm) {
+        dfree(m, m->enc_out); dfree(m, m->keys); dfree(m, m->mask);
+        RVB_CHECK(dmalloc(m, &m->enc_out, wv * Tm * ENC_OUT));
+        RVB_CHECK(dmalloc(m, &m->keys, wv * Tm * UNITS));
+        RVB_CHECK(dmalloc(m, &m->mask, wv * Tm));
+        m->ws_tm = Tm;
+    }
+    if ((size_t)S * W > m->ws_sw) {
+        dfree(m, m->step_ids); dfree(m, m->parent_ids);
+        RVB_CHECK(dmalloc(m, &m->step_ids, wv * S * W));
+        RVB_CHECK(dmalloc(m, &m->parent_ids, wv * S * W));
+        m->ws_sw = (size_t)S * W;
+    }
+    return RVB_OK;
+}
+
+// One encoder (raw: e = 0, event: e = 1) over nb snippets; final layer writes into
+// out[b, t_off + t, :] with row stride Tm*256 (basecaller.py:48-59, 405).
+static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, float *out, int Tm, int t_off, cudaStream_t s) {
+    const int feat = e == 0 ? 1 : 5;
+    float **yb = e == 0 ? m->y_raw : m->y_ev;
+    float *G = e == 0 ? m->G_raw : m->G_ev;
+    for (int l = 0; l < m->enc_depth; ++l) {
+        const bool last = (l == m->enc_depth - 1);
+        rec::Params p{};
+        p.x = x; p.G = G; p.wpack = m->d_rec[e][l];
+        p.state_in = l == 0 ? nullptr : m->st[e][(l - 1) & 1];
+        p.state_out = m->st[e][l & 1];
+        p.y = last ? out + (size_t)t_off * ENC_OUT : yb[l & 1];
+        p.y_bstride = last ? (long long)Tm * ENC_OUT : (long long)T * ENC_OUT;
+        p.B = nb; p.T = T;
+        if (l > 0) RVB_CHECK(project(m, yb[(l - 1) & 1], m->d_pw[e][l], m->d_pb[e][l], G, (long long)nb * T, 2 * GATES, ENC_OUT, s));
+        RVB_CHECK(rec::run(l == 0 ? feat : 0, p, s));
+    }
+    const long long n = (long long)nb * T;
+    input_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, feat, nb, T, m->mask, Tm, t_off);
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+
+static int check_inputs(rvb_model *m, const float *raw, int t_raw, const float *ev, int t_ev, int64_t batch, int *Tm) {
+    if (!m) return fail(RVB_ERR_ARG, "null model");
+    if (!m->finalized) return fail(RVB_ERR_STATE, "weights not finalised (call rvb_model_finalize)");
+    if (batch < 0) return fail(RVB_ERR_ARG, "negative batch");
+    const bool need_raw = m->input_kind != RVB_INPUT_EVENT, need_ev = m->input_kind != RVB_INPUT_RAW;
+    if (need_raw && (!raw || t_raw <= 0) && batch > 0) return fail(RVB_ERR_ARG, "raw input required");
+    if (need_ev && (!ev || t_ev <= 0) && batch > 0) return fail(RVB_ERR_ARG, "event input required");
+    *Tm = (need_raw ? t_raw : 0) + (need_ev ? t_ev : 0);
+    if (*Tm > 256) return fail(RVB_ERR_ARG, "memory length %d exceeds 256", *Tm);
+    return RVB_OK;
+}
+
+// encoders + mask + keys for one wave, into the handle's workspace
+static int encode_wave(rvb_model *m, const float *raw, int t_raw, const float *ev, int t_ev, int nb, int Tm, cudaStream_t s) {
+    const bool need_raw = m->input_kind != RVB_INPUT_EVENT, need_ev = m->input_kind != RVB_INPUT_RAW;
+    if (need_raw) RVB_CHECK(encode_branch(m, 0, raw, t_raw, nb, m->enc_out, Tm, 0, s));
+    if (need_ev) RVB_CHECK(encode_branch(m, 1, ev, t_ev, nb, m->enc_out, Tm, need_raw ? t_raw : 0, s));
+    return RVB_OK;
+}
+
+extern "C" int rvb_encode(rvb_model_t *m, const float *d_raw, int t_raw, const float *d_event, int t_event, int64_t batch,
+                          float *d_enc_out, uint8_t *d_mask, void *stream) {
+    int Tm = 0;
+    RVB_CHECK(check_inputs(m, d_raw, t_raw, d_event, t_event, batch, &Tm));
+    if (batch == 0) return RVB_OK;
+    if (!d_enc_out || !d_mask) return fail(RVB_ERR_ARG, "null output");
+    RVB_CUDA(cudaSetDevice(m->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool need_raw = m->input_kind != RVB_INPUT_EVENT, need_ev = m->input_kind != RVB_INPUT_RAW;
+    if (!need_raw) t_raw = 0;
+    if (!need_ev) t_event = 0;
+    RVB_CHECK(ensure_workspace(m, t_raw, t_event, 1, 1));
+    for (int64_t b0 = 0; b0 < batch; b0 += m->wave) {
+        const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
+        RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
+                              need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
+        RVB_CUDA(cudaMemcpyAsync(d_enc_out + (size_t)b0 * Tm * ENC_OUT, m->enc_out, (size_t)nb * Tm * ENC_OUT * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        RVB_CUDA(cudaMemcpyAsync(d_mask + (size_t)b0 * Tm, m->mask, (size_t)nb * Tm, cudaMemcpyDeviceToDevice, s));
+    }
+    return RVB_OK;
+}
+
+static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_event, int t_event, int64_t batch, int W,
+                  int max_output_len, bool beam, int32_t *d_ids, float *d_logits, float *d_scores, int32_t *d_step_ids,
+                  int32_t *d_parent_ids, int32_t *d_steps, cudaStream_t s) {
+    int Tm = 0;
+    RVB_CHECK(check_inputs(m, d_raw, t_raw, d_event, t_event, batch, &Tm));
+    const int S = max_output_len - 1;
+    if (!d_steps || !d_ids) return fail(RVB_ERR_ARG, "null output");
+    if (beam && (W < 1 || W > 9)) return fail(RVB_ERR_ARG, "beam_width must be in [1,9]");
+    RVB_CUDA(cudaSetDevice(m->device));
+    RVB_CUDA(cudaMemsetAsync(d_steps, 0, sizeof(int32_t), s));
+    if (batch == 0 || S <= 0) return RVB_OK;
+    const bool need_raw = m->input_kind != RVB_INPUT_EVENT, need_ev = m->input_kind != RVB_INPUT_RAW;
+    if (!need_raw) t_raw = 0;
+    if (!need_ev) t_event = 0;
+    RVB_CHECK(ensure_workspace(m, t_raw, t_event, S, W));
+    for (int64_t b0 = 0; b0 < batch; b0 += m->wave) {
+        const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
+        RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
+                              need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
+        RVB_CHECK(project(m, m->enc_out, m->d_wmem, nullptr, m->keys, (long long)nb * Tm, UNITS, ENC_OUT, s));
+        dec::Params p{};
+        p.keys = m->keys; p.values = m->enc_out; p.mask = m->mask;
+        p.wg = m->d_wg; p.wtok = m->d_wtok; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;
+        p.B = nb; p.Tm = Tm; p.W = W; p.S = S; p.beam = beam ? 1 : 0;
+        p.steps = d_steps;
+        if (beam) {
+            p.ids = d_ids + (size_t)b0 * S * W;
+            p.scores = d_scores + (size_t)b0 * S * W;
+            p.step_ids = d_step_ids ? d_step_ids + (size_t)b0 * S * W : m->step_ids;
+            p.parent_ids = d_parent_ids ? d_parent_ids + (size_t)b0 * S * W : m->parent_ids;
+        } else {
+            p.ids = d_ids + (size_t)b0 * S;
+            p.logits = d_logits + (size_t)b0 * S * VOCAB;
+        }
+        RVB_CHECK(dec::run(p, s));
+    }
+    return RVB_OK;
+}
+
+extern "C" int rvb_greedy(rvb_model_t *m, const float *d_raw, int t_raw, const float *d_event, int t_event, int64_t batch,
+                          int max_output_len, int32_t *d_ids, float *d_logits, int32_t *d_steps, void *stream) {
+    if (!d_logits) return fail(RVB_ERR_ARG, "null logits output");
+    return search(m, d_raw, t_raw, d_event, t_event, batch, 1, max_output_len, false, d_ids, d_logits, nullptr, nullptr,
+                  nullptr, d_steps, (cudaStream_t)stream);
+}
+
+extern "C" int rvb_beam(rvb_model_t *m, const float *d_raw, int t_raw, const float *d_event, int t_event, int64_t batch,
+                        int beam_width, int max_output_len, int32_t *d_pred_ids, float *d_scores, int32_t *d_step_ids,
+                        int32_t *d_parent_ids, int32_t *d_steps, void *stream) {
+    if (!d_scores) return fail(RVB_ERR_ARG, "null scores output");
+    return search(m, d_raw, t_raw, d_event, t_event, batch, beam_width, max_output_len, true, d_pred_ids, nullptr,
+                  d_scores, d_step_ids, d_parent_ids, d_steps, (cudaStream_t)stream);
+}
+
+// beam slot 0 of [B,S,W] -> [B,S]
+__global__ void slot0_kernel(const int32_t *ids, const float *sc, long long n, int W, int32_t *ids0, float *sc0) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ids0[i] = ids[i * W];
+    sc0[i] = sc[i * W];
+}
+
+extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, const float *h_event, int t_event, int64_t batch,
+                             int beam_width, int max_output_len, int32_t *h_ids, float *h_scores, int32_t *h_steps) {
+    int Tm = 0;
+    if (!m) return fail(RVB_ERR_ARG, "null model");
+    const bool need_raw = m->input_kind != RVB_INPUT_EVENT, need_ev = m->input_kind != RVB_INPUT_RAW;
+    RVB_CHECK(check_inputs(m, h_raw, t_raw, h_event, t_event, batch, &Tm));
+    if (!h_ids || !h_scores || !h_steps) return fail(RVB_ERR_ARG, "null output");
+    const int S = max_output_len - 1, W = beam_width;
+    *h_steps = 0;
+    if (batch == 0 || S <= 0) return RVB_OK;
+    if (W < 1 || W > 9) return fail(RVB_ERR_ARG, "beam_width must be in [1,9]");
+    RVB_CUDA(cudaSetDevice(m->device));
+    if (!m->hstream) RVB_CUDA(cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking));
+    cudaStream_t s = m->hstream;
+    // device-side I/O for one wave at a time (handle-owned, grown on demand)
+    const size_t wv = (size_t)m->wave;
+    const size_t need = wv * ((size_t)t_raw + (size_t)t_event * 5 + (size_t)S * W * 2 + (size_t)S * 2) + 64;
+    if (need > m->hb_cap) {
+        dfree(m, m->hb_raw);
+        RVB_CHECK(dmalloc(m, &m->hb_raw, need));
+        m->hb_cap = need;
+    }
+    float *d_raw = m->hb_raw;
+    float *d_ev = d_raw + wv * t_raw;
+    float *d_sc = d_ev + wv * t_event * 5;
+    int32_t *d_ids = reinterpret_cast<int32_t *>(d_sc + wv * S * W);
+    float *d_sc0 = reinterpret_cast<float *>(d_ids + wv * S * W);
+    int32_t *d_ids0 = reinterpret_cast<int32_t *>(d_sc0 + wv * S);
+    int32_t *d_steps = d_ids0 + wv * S;
+    RVB_CUDA(cudaMemsetAsync(d_steps, 0, sizeof(int32_t), s));
+    for (int64_t b0 = 0; b0 < batch; b0 += m->wave) {
+        const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
+        if (need_raw) RVB_CUDA(cudaMemcpyAsync(d_raw, h_raw + (size_t)b0 * t_raw, (size_t)nb * t_raw * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (need_ev) RVB_CUDA(cudaMemcpyAsync(d_ev, h_event + (size_t)b0 * t_event * 5, (size_t)nb * t_event * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
+        int32_t *tmp_steps = d_steps + 1;
+        RVB_CHECK(search(m, need_raw ? d_raw : nullptr, t_raw, need_ev ? d_ev : nullptr, t_event, nb, W, max_output_len, true,
+                         d_ids, nullptr, d_sc, nullptr, nullptr, tmp_steps, s));
+        // fold this wave's T into the running maximum and keep slot 0 only
+        const long long n = (long long)nb * S;
+        slot0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_ids, d_sc, n, W, d_ids0, d_sc0);
+        RVB_LAUNCH_CHECK();
+        count_launch();
+        RVB_CUDA(cudaMemcpyAsync(h_ids + (size_t)b0 * S, d_ids0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        RVB_CUDA(cudaMemcpyAsync(h_scores + (size_t)b0 * S, d_sc0, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        int32_t wave_steps = 0;
+        RVB_CUDA(cudaMemcpyAsync(&wave_steps, tmp_steps, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        RVB_CUDA(cudaStreamSynchronize(s));
+        if (wave_steps > *h_steps) *h_steps = wave_steps;
+    }
+    return RVB_OK;
+}
+
+extern "C" int rvb_project(const float *d_a, const float *d_b, const float *d_bias, float *d_c, int64_t mrows, int n, int k,
+                           int precision, void *stream) {
+    if (!d_a || !d_b || !d_c || mrows < 0 || n <= 0 || k <= 0) return fail(RVB_ERR_ARG, "project: bad argument");
+    if (precision == -1) return gemm::run_simt(d_a, d_b, d_bias, d_c, mrows, n, k, (cudaStream_t)stream);
+    if (!gemm::tc_available()) return fail(RVB_ERR_STATE, "tcgen05 projection kernel not built");
+    return gemm::run_tc(d_a, d_b, d_bias, d_c, mrows, n, k, precision, (cudaStream_t)stream);
+}

@@ -1,0 +1,65 @@
+// Shared helpers for libravvent_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/ravvent_b200.h"
+
+namespace rvb {
+
+// ---- thread-local error string + launch counter ---------------------------
+inline char *err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+inline int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+extern std::atomic<long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define RVB_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return rvb::fail(RVB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,      \
+                             cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define RVB_CHECK(expr)                    \
+    do {                                   \
+        int _s = (expr);                   \
+        if (_s != RVB_OK) return _s;       \
+    } while (0)
+
+#define RVB_LAUNCH_CHECK()                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess)                                                               \
+            return rvb::fail(RVB_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,  \
+                             cudaGetErrorString(_e));                                        \
+    } while (0)
+
+// ---- model constants (the kernels are specialised for the reference's shipped
+//      configuration: enc_units = dec_units = 128, vocab 7) -------------------
+constexpr int UNITS = 128;      // enc_units == dec_units
+constexpr int GATES = 4 * UNITS;
+constexpr int VOCAB = 7;
+constexpr int ENC_OUT = 2 * UNITS;
+constexpr int TOKEN_END = 1;    // '^'  data_loader.py:21
+constexpr int TOKEN_START = 2;  // '$'
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// tanh with full fp32 accuracy (the fp32-parity path must not use tanh.approx)
+__device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+}  // namespace rvb

@@ -1,0 +1,50 @@
+// Internal launch interfaces shared between the kernel translation units and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace rvb {
+
+namespace rec {     // K3, lstm_recurrent.cu
+struct Params {
+    const float *x;             // [B,T,F]           (layer 0)
+    const float *G;             // [B,T,2,512]       (layer > 0)
+    const float *wpack;         // [dir][rank][KX][4][64]
+    const float *state_in;      // [B,2,2,128] (dir, h|c) or nullptr == zeros
+    float *state_out;           // [B,2,2,128]
+    float *y;                   // (b,t,dir*128+u) at y[b*y_bstride + t*256 + dir*128 + u]
+    long long y_bstride;
+    int B, T;
+};
+int run(int feat, const Params &p, cudaStream_t stream);
+int kx_rows(int feat);
+}  // namespace rec
+
+namespace gemm {    // K2, proj_gemm.cu
+int run_simt(const float *A, const float *Bm, const float *bias, float *C, long long M, int N, int K, cudaStream_t s);
+int run_tc(const float *A, const float *Bm, const float *bias, float *C, long long M, int N, int K, int precision,
+           cudaStream_t s);
+bool tc_available();
+}  // namespace gemm
+
+namespace dec {     // K4 + K5, decoder.cu
+struct Params {
+    const float *keys;      // [B,Tm,128]
+    const float *values;    // [B,Tm,256]
+    const uint8_t *mask;    // [B,Tm]
+    const float *wg;        // [256][128][4]  rows 0..127: kernel rows of the attention input, 128..255: recurrent kernel
+    const float *wtok;      // [7][128][4]    kernel row of token v + bias
+    const float *watt;      // [384][128]
+    const float *wfc;       // [128][7]
+    const float *bfc;       // [7]
+    int B, Tm, W, S, beam;  // beam == 0: greedy (W == 1)
+    int32_t *ids;           // greedy sample_id [B,S]  | beam predicted_ids [B,S,W]
+    float *logits;          // greedy rnn_output [B,S,7]
+    float *scores;          // beam scores [B,S,W]
+    int32_t *step_ids;      // beam [B,S,W]
+    int32_t *parent_ids;    // beam [B,S,W]
+    int32_t *steps;         // atomicMax of T
+};
+int run(const Params &p, cudaStream_t stream);
+}  // namespace dec
+
+}  // namespace rvb

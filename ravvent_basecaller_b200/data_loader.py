@@ -1,0 +1,56 @@
+"""Inference-side constants and helpers of the reference's data_loader.py
+(constants :12-26; prepare_snippets / pad_input_snippets :70-111), with the
+heavy lifting on the GPU (EventDetector = K1, snippet builder kernels)."""
+from __future__ import annotations
+
+import numpy as np
+
+ED_WINDOW_LENGTH_1 = 6      # data_loader.py:12
+ED_WINDOW_LENGTH_2 = 9      # data_loader.py:13
+INPUT_PADDING = 0.          # data_loader.py:14
+MAX_RAW_LEN = 200           # data_loader.py:16
+MAX_EVENT_LEN = 30          # data_loader.py:17
+
+
+class CharTokenizer:
+    """Stand-in for the Keras Tokenizer the reference configures by hand
+    (data_loader.py:20-22): only word_index / index_word / sequences_to_texts /
+    texts_to_sequences are used on the inference path."""
+
+    def __init__(self, word_index):
+        self.word_index = dict(word_index)
+        self.index_word = {v: k for k, v in self.word_index.items()}
+
+    def sequences_to_texts(self, sequences):
+        # Keras joins the mapped words with ' ' and skips ids without a mapping
+        return [" ".join(self.index_word[int(i)] for i in seq if int(i) in self.index_word) for seq in sequences]
+
+    def texts_to_sequences(self, texts):
+        return [[self.word_index[ch] for ch in t.lower() if ch in self.word_index] for t in texts]
+
+
+nuc_tk = CharTokenizer({'': 0, '^': 1, '$': 2, 'a': 3, 'c': 4, 'g': 5, 't': 6})
+NUC_TOKEN_END = nuc_tk.word_index['^']
+NUC_TOKEN_START = nuc_tk.word_index['$']
+NUC_TOKEN_PAD = nuc_tk.word_index['']
+
+
+def unpack_data_to_input_target(data, input_data_type):
+    """utils.unpack_data_to_input_target (utils.py:34-43)."""
+    raw_sequence, events_sequence, target_sequence = data
+    if input_data_type == 'raw':
+        return raw_sequence, target_sequence
+    if input_data_type == 'event':
+        return events_sequence, target_sequence
+    if input_data_type == 'joint':
+        return (raw_sequence, events_sequence), target_sequence
+    raise ValueError(input_data_type)
+
+
+def calc_prob_logits_beam_search_scores(beam_scores):
+    """utils.calc_prob_logits_beam_search_scores (utils.py:123-128): per-base
+    probability exp(score[t] - score[t-1]) from cumulative beam scores."""
+    s = np.asarray(beam_scores.cpu() if hasattr(beam_scores, "cpu") else beam_scores)
+    prev = np.zeros_like(s)
+    prev[..., 1:] = s[..., :-1]
+    return np.exp(s - prev)
