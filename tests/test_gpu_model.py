@@ -157,9 +157,9 @@ def test_gather_tree_kernel_bit_exact():
     par = rng.integers(0, W, size=(T, B, W)).astype(np.int32)
     mx = rng.integers(0, T + 3, size=B).astype(np.int32)
     ref = mr.gather_tree(ids, par, mx)
-    d = lambda a: torch.from_numpy(a).cuda()
+    t_ids, t_par, t_mx = (torch.from_numpy(a).cuda() for a in (ids, par, mx))     # keep the tensors alive
     out = torch.empty((T, B, W), dtype=torch.int32, device="cuda")
-    _lib.check(_lib.lib.rvb_gather_tree(d(ids).data_ptr(), d(par).data_ptr(), d(mx).data_ptr(), T, B, W, 1, out.data_ptr(), None))
+    _lib.check(_lib.lib.rvb_gather_tree(t_ids.data_ptr(), t_par.data_ptr(), t_mx.data_ptr(), T, B, W, 1, out.data_ptr(), None))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), ref)
 
