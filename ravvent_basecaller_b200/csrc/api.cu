@@ -38,7 +38,7 @@ struct rvb_model {
     float *d_rec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_pw[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_pb[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    float *d_wmem = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
+    float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
     // workspace for one wave
     size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
     float *y_raw[2] = {nullptr, nullptr}, *y_ev[2] = {nullptr, nullptr};
@@ -212,6 +212,10 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
         RVB_CHECK(upload(m, &m->d_wg, wg));
         RVB_CHECK(upload(m, &m->d_wtok, wtok));
         RVB_CHECK(upload(m, &m->d_wmem, Wm->data));
+        std::vector<float> wmT((size_t)UNITS * ENC_OUT);
+        for (int e = 0; e < ENC_OUT; ++e)
+            for (int d = 0; d < UNITS; ++d) wmT[(size_t)d * ENC_OUT + e] = Wm->data[(size_t)e * UNITS + d];
+        RVB_CHECK(upload(m, &m->d_wmemT, wmT));
         RVB_CHECK(upload(m, &m->d_watt, Wa->data));
         RVB_CHECK(upload(m, &m->d_wfc, Wf->data));
         RVB_CHECK(upload(m, &m->d_bfc, Bf->data));
@@ -245,9 +249,8 @@ static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
         for (int e = 0; e < 2; ++e)
             for (int i = 0; i < 2; ++i) RVB_CHECK(dmalloc(m, &m->st[e][i], wv * 2 * 2 * UNITS));
     if ((size_t)Tm > m->ws_tm) {
-        dfree(m, m->enc_out); dfree(m, m->keys); dfree(m, m->mask);
+        dfree(m, m->enc_out); dfree(m, m->mask);
         RVB_CHECK(dmalloc(m, &m->enc_out, wv * Tm * ENC_OUT));
-        RVB_CHECK(dmalloc(m, &m->keys, wv * Tm * UNITS));
         RVB_CHECK(dmalloc(m, &m->mask, wv * Tm));
         m->ws_tm = Tm;
     }
@@ -346,9 +349,8 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
-        RVB_CHECK(project(m, m->enc_out, m->d_wmem, nullptr, m->keys, (long long)nb * Tm, UNITS, ENC_OUT, s));
         dec::Params p{};
-        p.keys = m->keys; p.values = m->enc_out; p.mask = m->mask;
+        p.wmemT = m->d_wmemT; p.values = m->enc_out; p.mask = m->mask;
         p.wg = m->d_wg; p.wtok = m->d_wtok; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;
         p.B = nb; p.Tm = Tm; p.W = W; p.S = S; p.beam = beam ? 1 : 0;
         p.steps = d_steps;

@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
     float *buf = smem;                       // [640][32]: 0..127 prev attention | 128..255 h | 256..511 context
     float *cs = buf + 640 * RMAX;            // [128][32]
     float *attn = cs + UNITS * RMAX;         // [128][32]
-    float *sc = attn + UNITS * RMAX;         // [32][TMAX]
-    float *wfc_s = sc + RMAX * TMAX;         // [128*7]
+    float *qs = attn + UNITS * RMAX;         // [256][32] folded query q' = W_mem . h
+    float *wfc_s = qs + ENC_OUT * RMAX;      // [128*7]
     float *logit_s = wfc_s + UNITS * VOCAB;  // [32][8]
     float *lp_s = logit_s + RMAX * 8;        // [32] beam log-probs
     float *nsc_s = lp_s + RMAX;              // [32] new scores
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
                 float4 w = __ldg(reinterpret_cast<const float4 *>(p.wtok + ((size_t)tok_s[half * 16 + r] * UNITS + u) * 4));
                 acc[r][0] = w.x; acc[r][1] = w.y; acc[r][2] = w.z; acc[r][3] = w.w;
             }
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 2 * UNITS; ++k) {
                 const float4 w = __ldg(reinterpret_cast<const float4 *>(p.wg + ((size_t)k * UNITS + u) * 4));
                 const float4 *xr = reinterpret_cast<const float4 *>(buf + k * RMAX + half * 16);
@@ -131,69 +131,124 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
         }
         __syncthreads();
 
-        // ---------------- phase 2: Luong score -> masked softmax -> context, one warp per snippet ----
+        // ---------------- phase 2a: q' = W_mem . h  (Luong score = keys.h = values.(W_mem.h)) ---------
+        // Folding the memory layer into the query means only `values` is streamed per step (A.3).
+        {
+            float acc[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) acc[r] = 0.0f;
+#pragma unroll 8
+            for (int k = 0; k < UNITS; ++k) {
+                const float w = __ldg(p.wmemT + (size_t)k * ENC_OUT + tid);
+                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RMAX);
+#pragma unroll
+                for (int q = 0; q < RMAX / 4; ++q) {
+                    const float4 x = xr[q];
+                    acc[q * 4 + 0] = fmaf(x.x, w, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(x.y, w, acc[q * 4 + 1]);
+                    acc[q * 4 + 2] = fmaf(x.z, w, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(x.w, w, acc[q * 4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RMAX / 4; ++q)
+                *reinterpret_cast<float4 *>(qs + tid * RMAX + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+        }
+        __syncthreads();
+
+        // ---------------- phase 2b: masked softmax(values.q') and context in ONE pass over values -----
+        // One warp per snippet, online softmax (running max / sum), all beams of the snippet share the
+        // stream.  Lane owns columns 4*lane..+3 and 128+4*lane..+3; rows are software-pipelined in
+        // groups of 4 (eight 128-bit loads in flight per lane, next group prefetched).
         for (int s = wid; s < ns; s += THREADS / 32) {
             const size_t bm = (size_t)(s0 + s) * Tm;
-            float hq[WMAX][4];
+            unsigned mbits = 0;                                   // validity of rows 8*lane .. 8*lane+7
 #pragma unroll
-            for (int w = 0; w < WMAX; ++w)
-                if (w < W) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) hq[w][e] = buf[(UNITS + 4 * lane + e) * RMAX + s * W + w];
-                }
-            for (int tt = 0; tt < Tm; ++tt) {
-                const float4 kv = __ldg(reinterpret_cast<const float4 *>(p.keys + (bm + tt) * UNITS + 4 * lane));
-                const bool valid = p.mask[bm + tt] != 0;
-#pragma unroll
-                for (int w = 0; w < WMAX; ++w)
-                    if (w < W) {
-                        float d = kv.x * hq[w][0] + kv.y * hq[w][1] + kv.z * hq[w][2] + kv.w * hq[w][3];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                        if (lane == 0) sc[(s * W + w) * TMAX + tt] = valid ? d : -INFINITY;
-                    }
+            for (int j = 0; j < 8; ++j) {
+                const int tt = 8 * lane + j;
+                if (tt < Tm && p.mask[bm + tt] != 0) mbits |= 1u << j;
             }
-            __syncwarp();
-            for (int w = 0; w < W; ++w) {
-                float *row = sc + (s * W + w) * TMAX;
-                float m = -INFINITY;
-                for (int tt = lane; tt < Tm; tt += 32) m = fmaxf(m, row[tt]);
+            float q[WMAX][8], acc[WMAX][8], mx[WMAX], den[WMAX];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                float sum = 0.0f;
-                for (int tt = lane; tt < Tm; tt += 32) { float e = __expf(row[tt] - m); row[tt] = e; sum += e; }
+            for (int w = 0; w < WMAX; ++w) {
+                mx[w] = -INFINITY; den[w] = 0.0f;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const float inv = 1.0f / sum;
-                for (int tt = lane; tt < Tm; tt += 32) row[tt] *= inv;
-            }
-            __syncwarp();
-            float ctx[WMAX][8];
-#pragma unroll
-            for (int w = 0; w < WMAX; ++w)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) ctx[w][e] = 0.0f;
-            for (int tt = 0; tt < Tm; ++tt) {
-                const float *vp = p.values + (bm + tt) * ENC_OUT + 4 * lane;
-                const float4 v0 = __ldg(reinterpret_cast<const float4 *>(vp));
-                const float4 v1 = __ldg(reinterpret_cast<const float4 *>(vp + UNITS));
-#pragma unroll
-                for (int w = 0; w < WMAX; ++w)
-                    if (w < W) {
-                        const float a = sc[(s * W + w) * TMAX + tt];
-                        ctx[w][0] = fmaf(a, v0.x, ctx[w][0]); ctx[w][1] = fmaf(a, v0.y, ctx[w][1]);
-                        ctx[w][2] = fmaf(a, v0.z, ctx[w][2]); ctx[w][3] = fmaf(a, v0.w, ctx[w][3]);
-                        ctx[w][4] = fmaf(a, v1.x, ctx[w][4]); ctx[w][5] = fmaf(a, v1.y, ctx[w][5]);
-                        ctx[w][6] = fmaf(a, v1.z, ctx[w][6]); ctx[w][7] = fmaf(a, v1.w, ctx[w][7]);
-                    }
-            }
-#pragma unroll
-            for (int w = 0; w < WMAX; ++w)
+                for (int e = 0; e < 8; ++e) { acc[w][e] = 0.0f; q[w][e] = 0.0f; }
                 if (w < W) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        buf[(2 * UNITS + 4 * lane + e) * RMAX + s * W + w] = ctx[w][e];
-                        buf[(3 * UNITS + 4 * lane + e) * RMAX + s * W + w] = ctx[w][4 + e];
+                        q[w][e] = qs[(4 * lane + e) * RMAX + s * W + w];
+                        q[w][4 + e] = qs[(UNITS + 4 * lane + e) * RMAX + s * W + w];
+                    }
+                }
+            }
+            const float *vbase = p.values + bm * ENC_OUT + 4 * lane;
+            float4 cur[8], nxt[8];
+            unsigned vb_cur = __shfl_sync(0xffffffffu, mbits, 0) & 0xFu, vb_nxt = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cur[2 * j] = cur[2 * j + 1] = make_float4(0, 0, 0, 0);
+                if ((vb_cur >> j) & 1u) {
+                    cur[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT));
+                    cur[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT + UNITS));
+                }
+            }
+            for (int t0 = 0; t0 < Tm; t0 += 4) {
+                const int t1 = t0 + 4;
+                vb_nxt = 0;
+                if (t1 < Tm) vb_nxt = (__shfl_sync(0xffffffffu, mbits, t1 >> 3) >> (t1 & 7)) & 0xFu;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    nxt[2 * j] = nxt[2 * j + 1] = make_float4(0, 0, 0, 0);
+                    if ((vb_nxt >> j) & 1u) {
+                        nxt[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT));
+                        nxt[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT + UNITS));
+                    }
+                }
+                if (vb_cur != 0) {
+#pragma unroll
+                    for (int w = 0; w < WMAX; ++w)
+                        if (w < W) {
+                            float sj[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 a = cur[2 * j], b = cur[2 * j + 1];
+                                float d = a.x * q[w][0] + a.y * q[w][1] + a.z * q[w][2] + a.w * q[w][3] +
+                                          b.x * q[w][4] + b.y * q[w][5] + b.z * q[w][6] + b.w * q[w][7];
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                                sj[j] = ((vb_cur >> j) & 1u) ? d : -INFINITY;
+                            }
+                            const float mn = fmaxf(fmaxf(mx[w], fmaxf(sj[0], sj[1])), fmaxf(sj[2], sj[3]));
+                            const float scale = __expf(mx[w] - mn);          // mx == -inf -> 0
+                            float pj[4], ps = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { pj[j] = __expf(sj[j] - mn); ps += pj[j]; }
+                            den[w] = den[w] * scale + ps;
+                            mx[w] = mn;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[w][e] *= scale;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float4 a = cur[2 * j], b = cur[2 * j + 1];
+                                acc[w][0] = fmaf(pj[j], a.x, acc[w][0]); acc[w][1] = fmaf(pj[j], a.y, acc[w][1]);
+                                acc[w][2] = fmaf(pj[j], a.z, acc[w][2]); acc[w][3] = fmaf(pj[j], a.w, acc[w][3]);
+                                acc[w][4] = fmaf(pj[j], b.x, acc[w][4]); acc[w][5] = fmaf(pj[j], b.y, acc[w][5]);
+                                acc[w][6] = fmaf(pj[j], b.z, acc[w][6]); acc[w][7] = fmaf(pj[j], b.w, acc[w][7]);
+                            }
+                        }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+                vb_cur = vb_nxt;
+            }
+#pragma unroll
+            for (int w = 0; w < WMAX; ++w)
+                if (w < W) {
+                    // every position masked: tfa's softmax over all -inf yields NaN; keep that contract
+                    const float inv = (den[w] > 0.0f) ? 1.0f / den[w] : __int_as_float(0x7fc00000);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        buf[(2 * UNITS + 4 * lane + e) * RMAX + s * W + w] = acc[w][e] * inv;
+                        buf[(3 * UNITS + 4 * lane + e) * RMAX + s * W + w] = acc[w][4 + e] * inv;
                     }
                 }
         }
@@ -204,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
             float acc[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = 0; k < 3 * UNITS; ++k) {
                 const float w = __ldg(p.watt + (size_t)k * UNITS + u);
                 const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RMAX + half * 16);
@@ -352,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
     }
 }
 
-constexpr size_t SMEM_FLOATS = 640 * RMAX + 2 * UNITS * RMAX + RMAX * TMAX + UNITS * VOCAB + RMAX * 8 + 2 * RMAX + 6 * RMAX;
+constexpr size_t SMEM_FLOATS = 640 * RMAX + 2 * UNITS * RMAX + ENC_OUT * RMAX + UNITS * VOCAB + RMAX * 8 + 2 * RMAX + 6 * RMAX;
 
 int run(const Params &p, cudaStream_t stream) {
     if (p.B <= 0 || p.S <= 0) return RVB_OK;

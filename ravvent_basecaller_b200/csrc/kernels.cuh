@@ -28,7 +28,7 @@ bool tc_available();
 
 namespace dec {     // K4 + K5, decoder.cu
 struct Params {
-    const float *keys;      // [B,Tm,128]
+    const float *wmemT;     // [128][256] transposed Luong memory layer (keys are never materialised)
     const float *values;    // [B,Tm,256]
     const uint8_t *mask;    // [B,Tm]
     const float *wg;        // [256][128][4]  rows 0..127: kernel rows of the attention input, 128..255: recurrent kernel
