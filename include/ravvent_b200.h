@@ -112,6 +112,9 @@ int rvb_model_destroy(rvb_model_t *m);
 int rvb_model_set_weight(rvb_model_t *m, const char *name, const float *h_data,
                          const int64_t *shape, int ndim);
 int rvb_model_finalize(rvb_model_t *m);
+/* Synchronises the device and reports device-side failures of earlier asynchronous calls
+ * (e.g. a tensor-core pipeline that timed out).  RVB_OK when everything completed. */
+int rvb_model_check(rvb_model_t *m);
 
 /* K2+K3  Basecaller._encode_input (basecaller.py:395-416; Encoder.call :48-59).
  * d_raw [B,t_raw,1] / d_event [B,t_event,5] float32 (either may be NULL per

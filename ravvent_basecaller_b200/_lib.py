@@ -22,7 +22,7 @@ class RavventError(RuntimeError):
 
 if not _SO.exists():
     raise ImportError(
-        f"{_SO} is missing. Build it with `python -m ravvent_basecaller_b200.build` "
+        f"{_SO} is missing. Build it with `python ravvent_basecaller_b200/build.py` "
         "(needs nvcc; sm_100a). This package has no CPU or PyTorch fallback.")
 
 lib = C.CDLL(str(_SO))
@@ -40,6 +40,7 @@ _PROTOS = {
     "rvb_model_destroy": (_i, [_p]),
     "rvb_model_set_weight": (_i, [_p, C.c_char_p, _p, _p, _i]),
     "rvb_model_finalize": (_i, [_p]),
+    "rvb_model_check": (_i, [_p]),
     "rvb_encode": (_i, [_p, _p, _i, _p, _i, _i64, _p, _p, _p]),
     "rvb_greedy": (_i, [_p, _p, _i, _p, _i, _i64, _i, _p, _p, _p, _p]),
     "rvb_beam": (_i, [_p, _p, _i, _p, _i, _i64, _i, _i, _p, _p, _p, _p, _p, _p]),

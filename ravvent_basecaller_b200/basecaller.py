@@ -143,6 +143,7 @@ class Basecaller:
             mask = torch.empty((B, Tm), dtype=torch.uint8, device=self.device)
             _lib.check(_lib.lib.rvb_encode(self._h, self._ptr(raw), t_raw, self._ptr(event), t_ev, B,
                                            enc.data_ptr(), mask.data_ptr(), self._stream()))
+        _lib.check(_lib.lib.rvb_model_check(self._h))
         mask = mask.bool()
         if host:
             return enc.cpu().numpy(), mask.cpu().numpy()
@@ -163,6 +164,7 @@ class Basecaller:
             _lib.check(_lib.lib.rvb_greedy(self._h, self._ptr(raw), t_raw, self._ptr(event), t_ev, B, int(max_output_len),
                                            ids.data_ptr(), logits.data_ptr(), steps.data_ptr(), self._stream()))
             T = int(steps.item())
+            _lib.check(_lib.lib.rvb_model_check(self._h))
         ids, logits = ids[:, :T], logits[:, :T]
         if host:
             return ids.cpu().numpy(), logits.cpu().numpy()
@@ -200,6 +202,7 @@ class Basecaller:
                                          ids.data_ptr(), scores.data_ptr(), step_ids.data_ptr(), parents.data_ptr(),
                                          steps.data_ptr(), self._stream()))
             T = int(steps.item())
+            _lib.check(_lib.lib.rvb_model_check(self._h))
         if return_all_beams:
             out = (ids[:, :T], scores[:, :T], step_ids[:, :T], parents[:, :T])
             return tuple(o.cpu().numpy() for o in out) if host else out

@@ -1,6 +1,6 @@
 """In-tree build of libravvent_b200.so (nvcc, sm_100a only).
 
-    python -m ravvent_basecaller_b200.build [--force]
+    python ravvent_basecaller_b200/build.py [--force]     (or __graft_entry__.build())
 
 The library is linked against the static CUDA runtime, so it loads on a machine
 without a GPU (compute calls then fail with RVB_ERR_CUDA - there is no CPU path).

@@ -38,6 +38,9 @@ struct rvb_model {
     float *d_rec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_pw[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_pb[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float *d_phi[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // tf32 hi part, [N,K]
+    float *d_plo[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // remainder, [N,K]
+    int *d_abort = nullptr;
     float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
     // workspace for one wave
     size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
@@ -187,7 +190,13 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
                 }
             }
             RVB_CHECK(upload(m, &m->d_rec[e][l], pack));
-            if (l > 0) { RVB_CHECK(upload(m, &m->d_pw[e][l], wcat)); RVB_CHECK(upload(m, &m->d_pb[e][l], bcat)); }
+            if (l > 0) {
+                RVB_CHECK(upload(m, &m->d_pw[e][l], wcat));
+                RVB_CHECK(upload(m, &m->d_pb[e][l], bcat));
+                RVB_CHECK(dmalloc(m, &m->d_phi[e][l], wcat.size()));
+                RVB_CHECK(dmalloc(m, &m->d_plo[e][l], wcat.size()));
+                RVB_CHECK(gemm::prepare_weights(m->d_pw[e][l], m->d_phi[e][l], m->d_plo[e][l], ENC_OUT, 2 * GATES, nullptr));
+            }
         }
     }
     {
@@ -220,14 +229,17 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
         RVB_CHECK(upload(m, &m->d_wfc, Wf->data));
         RVB_CHECK(upload(m, &m->d_bfc, Bf->data));
     }
+    if (!m->d_abort) { RVB_CHECK(dmalloc(m, &m->d_abort, 1)); }
+    RVB_CUDA(cudaMemset(m->d_abort, 0, sizeof(int)));
+    RVB_CUDA(cudaDeviceSynchronize());
     m->finalized = true;
     return RVB_OK;
 }
 
-static int project(rvb_model *m, const float *A, const float *W, const float *bias, float *C, long long M, int N, int K,
-                   cudaStream_t s) {
-    if (m->use_tc) return gemm::run_tc(A, W, bias, C, M, N, K, m->precision, s);
-    return gemm::run_simt(A, W, bias, C, M, N, K, s);
+static int project(rvb_model *m, int e, int l, const float *A, float *C, long long M, cudaStream_t s) {
+    if (m->use_tc)
+        return gemm::run_tc(A, m->d_phi[e][l], m->d_plo[e][l], m->d_pb[e][l], C, M, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s);
+    return gemm::run_simt(A, m->d_pw[e][l], m->d_pb[e][l], C, M, 2 * GATES, ENC_OUT, s);
 }
 
 static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
@@ -278,7 +290,7 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
         p.y = last ? out + (size_t)t_off * ENC_OUT : yb[l & 1];
         p.y_bstride = last ? (long long)Tm * ENC_OUT : (long long)T * ENC_OUT;
         p.B = nb; p.T = T;
-        if (l > 0) RVB_CHECK(project(m, yb[(l - 1) & 1], m->d_pw[e][l], m->d_pb[e][l], G, (long long)nb * T, 2 * GATES, ENC_OUT, s));
+        if (l > 0) RVB_CHECK(project(m, e, l, yb[(l - 1) & 1], G, (long long)nb * T, s));
         RVB_CHECK(rec::run(l == 0 ? feat : 0, p, s));
     }
     const long long n = (long long)nb * T;
@@ -391,6 +403,8 @@ __global__ void slot0_kernel(const int32_t *ids, const float *sc, long long n, i
     sc0[i] = sc[i * W];
 }
 
+extern "C" int rvb_model_check(rvb_model_t *m);
+
 extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, const float *h_event, int t_event, int64_t batch,
                              int beam_width, int max_output_len, int32_t *h_ids, float *h_scores, int32_t *h_steps) {
     int Tm = 0;
@@ -440,13 +454,40 @@ extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, cons
         RVB_CUDA(cudaStreamSynchronize(s));
         if (wave_steps > *h_steps) *h_steps = wave_steps;
     }
+    return rvb_model_check(m);
+}
+
+extern "C" int rvb_model_check(rvb_model_t *m) {
+    if (!m) return fail(RVB_ERR_ARG, "null model");
+    RVB_CUDA(cudaSetDevice(m->device));
+    RVB_CUDA(cudaDeviceSynchronize());
+    int flag = 0;
+    if (m->d_abort) RVB_CUDA(cudaMemcpy(&flag, m->d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag != 0) return fail(RVB_ERR_INTERNAL, "a tcgen05 projection kernel timed out on an mbarrier (results invalid)");
     return RVB_OK;
 }
 
 extern "C" int rvb_project(const float *d_a, const float *d_b, const float *d_bias, float *d_c, int64_t mrows, int n, int k,
                            int precision, void *stream) {
     if (!d_a || !d_b || !d_c || mrows < 0 || n <= 0 || k <= 0) return fail(RVB_ERR_ARG, "project: bad argument");
-    if (precision == -1) return gemm::run_simt(d_a, d_b, d_bias, d_c, mrows, n, k, (cudaStream_t)stream);
-    if (!gemm::tc_available()) return fail(RVB_ERR_STATE, "tcgen05 projection kernel not built");
-    return gemm::run_tc(d_a, d_b, d_bias, d_c, mrows, n, k, precision, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == -1) return gemm::run_simt(d_a, d_b, d_bias, d_c, mrows, n, k, s);
+    if (precision != RVB_PREC_FP32 && precision != RVB_PREC_BF16) return fail(RVB_ERR_ARG, "project: bad precision");
+    // standalone entry (tests / roofline): split + transpose the weights into scratch, run, check the abort flag
+    float *scratch = nullptr;
+    RVB_CUDA(cudaMalloc(&scratch, ((size_t)2 * n * k + 16) * sizeof(float)));
+    float *hiT = scratch, *loT = scratch + (size_t)n * k;
+    int *flag = reinterpret_cast<int *>(scratch + (size_t)2 * n * k);
+    int st = RVB_OK;
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), s);
+    if (e != cudaSuccess) st = fail(RVB_ERR_CUDA, "memset: %s", cudaGetErrorString(e));
+    if (st == RVB_OK) st = gemm::prepare_weights(d_b, hiT, loT, k, n, s);
+    if (st == RVB_OK) st = gemm::run_tc(d_a, hiT, loT, d_bias, d_c, mrows, n, k, precision, flag, s);
+    int h_flag = 0;
+    e = cudaStreamSynchronize(s);
+    if (st == RVB_OK && e != cudaSuccess) st = fail(RVB_ERR_CUDA, "project: %s", cudaGetErrorString(e));
+    if (st == RVB_OK) cudaMemcpy(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(scratch);
+    if (st == RVB_OK && h_flag != 0) st = fail(RVB_ERR_INTERNAL, "project: tcgen05 kernel timed out on an mbarrier");
+    return st;
 }

@@ -21,8 +21,10 @@ int kx_rows(int feat);
 
 namespace gemm {    // K2, proj_gemm.cu
 int run_simt(const float *A, const float *Bm, const float *bias, float *C, long long M, int N, int K, cudaStream_t s);
-int run_tc(const float *A, const float *Bm, const float *bias, float *C, long long M, int N, int K, int precision,
-           cudaStream_t s);
+// tcgen05 path: WhiT / WloT are the [N,K] tf32 hi / remainder parts made by prepare_weights
+int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaStream_t s);
+int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
+           int precision, int *abort_flag, cudaStream_t s);
 bool tc_available();
 }  // namespace gemm
 

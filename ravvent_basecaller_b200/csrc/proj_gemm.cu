@@ -10,6 +10,8 @@
 //     device (tests call both through rvb_project) and as the exact-fp32 reference
 //     when debugging; the model path never selects it implicitly.
 #include "kernels.cuh"
+#define RVB_HAVE_TC 1
+#include "proj_gemm_tc.cuh"
 
 namespace rvb {
 namespace gemm {
@@ -89,12 +91,37 @@ int run_simt(const float *A, const float *Bm, const float *bias, float *C, long 
     return RVB_OK;
 }
 
-#ifndef RVB_HAVE_TC
-bool tc_available() { return false; }
-int run_tc(const float *, const float *, const float *, float *, long long, int, int, int, cudaStream_t) {
-    return fail(RVB_ERR_STATE, "tcgen05 projection kernel not built");
+bool tc_available() { return true; }
+
+// W[K,N] row-major -> tf32-exact hi part and remainder, both transposed to [N,K] (K-major B operand).
+__global__ void split_transpose_kernel(const float *__restrict__ W, float *__restrict__ hiT, float *__restrict__ loT, int K, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const int n = i / K, k = i % K;
+    const float v = W[(size_t)k * N + n];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hiT[i] = h;
+    loT[i] = v - h;
 }
-#endif
+
+int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaStream_t stream) {
+    const int n = K * N;
+    split_transpose_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W, hiT, loT, K, N);
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+
+int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
+           int precision, int *abort_flag, cudaStream_t stream) {
+    if (M <= 0) return RVB_OK;
+    if (N % 128 != 0 || K % tc::BK != 0) return fail(RVB_ERR_ARG, "gemm_tc: N %% 128 and K %% 32 must be 0 (N=%d K=%d)", N, K);
+    const bool three = (precision == RVB_PREC_FP32);
+    if (N % 256 == 0) return three ? tc::launch<256, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
+                                   : tc::launch<256, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+    return three ? tc::launch<128, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
+                 : tc::launch<128, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+}
 
 }  // namespace gemm
 }  // namespace rvb

@@ -1,0 +1,301 @@
+// K2 on the 5th-generation tensor cores:  C[M,N] = A[M,K] * W[K,N] (+ bias[N]),  fp32 in / fp32 out.
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a ring of shared-memory
+//     stages, accumulators in TMEM, MMAs issued by one elected thread (tcgen05.mma kind::tf32),
+//     accumulators read back with tcgen05.ld for the bias epilogue;
+//   * fp32 parity ("3xTF32"): A = A_hi + A_lo and W = W_hi + W_lo with *_hi exactly representable in
+//     tf32; D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi recovers ~2^-21 relative accuracy on the tf32
+//     pipe.  W is split once on the host; A is split per stage by four "split" warps between the TMA
+//     landing and the MMA issue (in place for hi, a sibling buffer for lo; the swizzled placement is
+//     irrelevant to an element-wise pass);
+//   * NPASS = 1 skips the split (single tf32 pass) -- used by the bf16-tolerance mode.
+//
+// Tile: 128 rows x BN columns per CTA, BK = 32 fp32 (= one 128-byte swizzle row) per stage.
+// Warp roles (256 threads): w0 = TMA producer, w1 = TMEM allocator + MMA issuer, w4..w7 = A split
+// and epilogue (TMEM lane quarter = warp % 4).  Every mbarrier wait is bounded: on a timeout the
+// kernel raises a flag and drains instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace rvb {
+namespace gemm {
+namespace tc {
+
+constexpr int BM = 128, BK = 32, THREADS = 256;
+constexpr int UMMA_K = 8;                   // tf32: 32 bytes of K per instruction
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait; returns false (and the caller drains) if the phase never completes.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *abort_flag) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return true;
+        if ((it & 1023u) == 1023u && *reinterpret_cast<volatile int *>(abort_flag) != 0) return false;
+    }
+    atomicExch(abort_flag, 1);
+    return false;
+}
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major; 1) |
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+template <int BN, int NPASS>
+struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 4;                  // 16 KB
+    static constexpr int B_BYTES = BN * BK * 4;
+    static constexpr int STAGE_BYTES = (NPASS == 3) ? (2 * A_BYTES + 2 * B_BYTES) : (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (NPASS == 3) ? ((BN == 256) ? 2 : 3) : 4;
+    static constexpr int TX_BYTES = A_BYTES + ((NPASS == 3) ? 2 : 1) * B_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+               const __grid_constant__ CUtensorMap map_blo, const float *__restrict__ bias, float *__restrict__ C,
+               long long M, int N, int K, int *abort_flag) {
+    using cfg = Cfg<BN, NPASS>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t *full = bars;                         // TMA landed
+    uint64_t *ready = bars + cfg::STAGES;          // A split done (NPASS == 3)
+    uint64_t *empty = bars + 2 * cfg::STAGES;      // MMAs of the stage retired
+    uint64_t *acc_full = bars + 3 * cfg::STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * cfg::STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = N / BN;
+    const int n_tile = (int)(blockIdx.x % n_tiles), m_tile = (int)(blockIdx.x / n_tiles);
+    const int num_kb = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto stage_a = [&](int s) { return smem + (size_t)s * cfg::STAGE_BYTES; };
+    auto stage_bhi = [&](int s) { return stage_a(s) + ((NPASS == 3) ? 2 : 1) * cfg::A_BYTES; };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
+                if (round > 0 && !mbar_wait(&empty[s], (round - 1) & 1, abort_flag)) break;
+                mbar_expect_tx(&full[s], cfg::TX_BYTES);
+                tma_load_2d(&map_a, &full[s], stage_a(s), kb * BK, m_tile * BM);
+                tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kb * BK, n_tile * BN);
+                if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kb * BK, n_tile * BN);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            bool ok = true;
+            for (int kb = 0; kb < num_kb && ok; ++kb) {
+                const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
+                ok = mbar_wait((NPASS == 3) ? &ready[s] : &full[s], round & 1, abort_flag);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_bhi(s));
+#pragma unroll
+                for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                    const uint32_t koff = ks * UMMA_K * 4;           // bytes along K inside the swizzle row
+                    const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                    if (NPASS == 3) {
+                        umma_tf32(tmem_base, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
+                        umma_tf32(tmem_base, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
+                        umma_tf32(tmem_base, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+                    }
+                }
+                umma_commit(&empty[s]);            // frees the stage when these MMAs retire
+            }
+            umma_commit(acc_full);                 // arrives when every MMA above has retired
+        }
+    } else if (warp >= 4) {
+        const int et = threadIdx.x - 128;          // 0..127
+        bool ok = true;
+        if (NPASS == 3) {
+            // ===================== A split: hi in place, lo to the sibling buffer =====================
+            for (int kb = 0; kb < num_kb && ok; ++kb) {
+                const int s = kb % cfg::STAGES, round = kb / cfg::STAGES;
+                ok = mbar_wait(&full[s], round & 1, abort_flag);
+                if (!ok) break;
+                float4 *hi = reinterpret_cast<float4 *>(stage_a(s));
+                float4 *lo = reinterpret_cast<float4 *>(stage_a(s) + cfg::A_BYTES);
+#pragma unroll
+                for (int i = 0; i < cfg::A_BYTES / 16 / 128; ++i) {
+                    float4 v = hi[et + i * 128];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[et + i * 128] = h;
+                    lo[et + i * 128] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                mbar_arrive(&ready[s]);
+            }
+        }
+        // ===================== epilogue: TMEM -> registers -> (+bias) -> global =====================
+        if (ok) ok = mbar_wait(acc_full, 0, abort_flag);
+        if (ok) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int q = warp & 3;                                  // TMEM lane quarter of this warp
+            const long long row = (long long)m_tile * BM + q * 32 + lane;
+            float *crow = C + row * N + (size_t)n_tile * BN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        if (bias != nullptr) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)n_tile * BN + c0 + j));
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        *reinterpret_cast<float4 *>(crow + c0 + j) = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] tensor, box = BK columns x box_rows rows, 128-byte swizzle.
+inline int make_map(CUtensorMap *map, const float *base, long long rows, int cols, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return RVB_OK;
+}
+
+template <int BN, int NPASS>
+int launch(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
+           int *abort_flag, cudaStream_t stream) {
+    using cfg = Cfg<BN, NPASS>;
+    CUtensorMap ma, mh, ml;
+    RVB_CHECK(make_map(&ma, A, M, K, BM));
+    RVB_CHECK(make_map(&mh, WhiT, N, K, BN));
+    RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, BN));
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+    const long long tiles = (long long)(N / BN) * ((M + BM - 1) / BM);
+    if (tiles > 0x7fffffffLL) return fail(RVB_ERR_ARG, "projection too large for one launch");
+    dim3 grid((unsigned)tiles);
+    gemm_tc_kernel<BN, NPASS><<<grid, THREADS, cfg::SMEM, stream>>>(ma, mh, ml, bias, C, M, N, K, abort_flag);
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+
+}  // namespace tc
+}  // namespace gemm
+}  // namespace rvb

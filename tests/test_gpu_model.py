@@ -164,19 +164,29 @@ def test_gather_tree_kernel_bit_exact():
     assert np.array_equal(out.cpu().numpy(), ref)
 
 
-@pytest.mark.parametrize("prec", [-1])
+@pytest.mark.parametrize("prec", [-1, 0, 1])
 def test_projection_kernel(prec):
+    """K2 through rvb_project.  prec -1: FFMA validation kernel; 0: tcgen05 3xTF32 (fp32 parity);
+    1: tcgen05 single tf32 pass (bf16-tolerance mode)."""
     from ravvent_basecaller_b200 import _lib
     rng = np.random.default_rng(5)
-    for M, N, K in [(1000, 1024, 256), (257, 128, 256), (64, 128, 384)]:
+    for M, N, K in [(1000, 1024, 256), (257, 128, 256), (64, 128, 384), (128 * 300 + 5, 1024, 256)]:
         a = rng.normal(size=(M, K)).astype(np.float32); b = (rng.normal(size=(K, N)) * 0.1).astype(np.float32)
         bias = rng.normal(size=N).astype(np.float32)
         ta, tb, tbias = (torch.from_numpy(v).cuda() for v in (a, b, bias))
-        c = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        c = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda")
         _lib.check(_lib.lib.rvb_project(ta.data_ptr(), tb.data_ptr(), tbias.data_ptr(), c.data_ptr(), M, N, K, prec, None))
         torch.cuda.synchronize()
         ref = a.astype(np.float64) @ b.astype(np.float64) + bias
-        np.testing.assert_allclose(c.cpu().numpy(), ref, rtol=1e-4, atol=1e-4)
+        got = c.cpu().numpy()
+        err = np.abs(got - ref).max()
+        # |a||b| row/col norms ~ 16 * 1.6: fp32-level error ~1e-5, tf32 single pass ~1e-2
+        assert np.isfinite(got).all(), (M, N, K, np.isnan(got).mean())
+        assert err < (5e-5 if prec <= 0 else 3e-2), (M, N, K, err)
+        c2 = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib.rvb_project(ta.data_ptr(), tb.data_ptr(), None, c2.data_ptr(), M, N, K, prec, None))
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(c2.cpu().numpy() + bias, got, rtol=0, atol=1e-5)
 
 
 def test_error_paths():
