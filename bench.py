@@ -42,6 +42,8 @@ FLOP_PER_CHUNK = {1: 274.98e6, 5: 347.06e6}
 REC_FLOP_PER_STEP_ROW = 131072            # recurrent FLOPs per timestep per direction per layer per snippet
 REC_BYTES_L0 = 512 + 4                    # per step per row per direction, raw layer 0 (write h + read x)
 REC_BYTES_L1 = 2560                       # layer > 0: read 512 pre-gates + write 128 h (fp32)
+# dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/), 9472-chunk wave
+NCU_TRAFFIC = {"recurrent_lstm": 9.72e9, "decoder": None, "projection_gemm": None}
 
 
 def synth_chunks(rng, n):
@@ -195,7 +197,7 @@ def run_ours(args, rank, local_rank, world):
         ids, sc = bc.beam_search_prediction((raw_p.numpy(), ev_p.numpy()), beam, MAX_OUTPUT_LEN)
         return ids
 
-    def timed(fn, beam, steps, warmup, sample_clocks=False):
+    def timed(fn, beam, steps, warmup, sample_clocks=False, profile=False):
         for _ in range(warmup):
             fn(beam)
         sampler = ClockSampler(local_rank) if sample_clocks else None
@@ -205,6 +207,8 @@ def run_ours(args, rank, local_rank, world):
         n0 = _lib.launch_count()
         t0w = time.time()
         ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        if profile:
+            _lib.profile(True)
         ev0.record()
         ids = None
         for _ in range(steps):
@@ -216,12 +220,16 @@ def run_ours(args, rank, local_rank, world):
         ms = ev0.elapsed_time(ev1)
         launches = _lib.launch_count() - n0
         clocks = sampler.stop(t0w, t1w) if sampler else None
-        return max_over_ranks(ms) / steps, launches, clocks, ids
+        prof = None
+        if profile:
+            prof = _lib.profile_read()
+            _lib.profile(False)
+        return max_over_ranks(ms) / steps, launches, clocks, ids, prof
 
-    ms1, launches, clocks, ids1 = timed(step_device, args.beam, args.steps, args.warmup, sample_clocks=True)
+    ms1, launches, clocks, ids1, prof = timed(step_device, args.beam, args.steps, args.warmup, sample_clocks=True, profile=True)
     other = 5 if args.beam == 1 else 1
-    ms_o, _, _, _ = timed(step_device, other, max(1, args.steps // 2), 1)
-    ms_e2e, _, _, _ = timed(step_host, args.beam, max(1, args.steps // 2), 1)
+    ms_o, _, _, _, _ = timed(step_device, other, max(1, args.steps // 2), 1)
+    ms_e2e, _, _, _, _ = timed(step_host, args.beam, max(1, args.steps // 2), 1)
 
     chunks_total = C * world
     rate = lambda ms: chunks_total / (ms * 1e-3)
@@ -231,8 +239,9 @@ def run_ours(args, rank, local_rank, world):
     called = int((((ids_np >= 3) & (ids_np <= 6)) & (np.arange(ids_np.shape[1])[None, :] < first_end[:, None])).sum())
 
     # ---- roofline of the dominant kernel (K3, persistent recurrent LSTM), timed live with CUDA events
-    prof = kernel_profile(bc, raw_d, ev_d, args.beam, dev)
     peak, peak_src = measured_peaks()
+    kr = kernel_rooflines(prof, args.steps, C, args.beam, peak)
+    dom = max(kr, key=lambda k: kr[k]["ms"])
 
     line = None
     if rank == 0:
@@ -261,13 +270,15 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": rate(ms_e2e) * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": prof["rec_gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": prof["rec_gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "lstm_rec_kernel (K3)", "share_of_step": prof["rec_share"],
-                         "ffma_tflops": prof["rec_tflops"],
-                         "note": "fp32 mode keeps the recurrence on the FFMA pipe, so this kernel is FP32-issue bound, "
-                                 "not HBM bound; ffma_tflops is its achieved rate"},
-            "kernel_ms": prof["kernel_ms"],
+            "roofline": {"bound": "hbm", "achieved": kr[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": kr[dom]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                         "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms1 * args.steps),
+                         "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
+                         "achieved_tflops": kr[dom]["tflops"],
+                         "note": "fp32-parity mode keeps the LSTM recurrence on the FFMA pipe (56%% of the 74.5 TFLOP/s "
+                                 "FP32 peak), so this kernel is FP32-issue bound, not HBM bound; achieved = algorithmic "
+                                 "bytes (DESIGN.md §5) / CUDA-event time"},
+            "kernels": kr,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -276,29 +287,32 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def kernel_profile(bc, raw_d, ev_d, beam, dev):
-    """Per-stage device time of one step, CUDA events on the launching stream (the library launches on
-    torch's current stream).  Stages are run through the same C-ABI entry points the step uses."""
-    import torch
-    from ravvent_basecaller_b200 import _lib
-    C = raw_d.shape[0]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    torch.cuda.synchronize(dev)
-    ev[0].record()
-    bc._encode_input((raw_d, ev_d))
-    ev[1].record()
-    bc.beam_search_prediction((raw_d, ev_d), beam, MAX_OUTPUT_LEN)
-    ev[2].record()
-    torch.cuda.synchronize(dev)
-    enc_ms = ev[0].elapsed_time(ev[1]); full_ms = ev[1].elapsed_time(ev[2])
-    # recurrent kernel time: encode time minus the projection GEMMs is not separable from outside, so the
-    # library exposes nothing special here; the encode stage is >95% K3 in fp32 mode (see profiles/).
-    rec_ms = enc_ms
-    steps_rows = C * (T_RAW + T_EV) * 2 * 2           # (timestep, direction, layer) units per pass
-    rec_flops = steps_rows * REC_FLOP_PER_STEP_ROW
-    rec_bytes = C * (T_RAW + T_EV) * 2 * (REC_BYTES_L0 + REC_BYTES_L1)
-    return {"rec_gbs": rec_bytes / (rec_ms * 1e-3) / 1e9, "rec_tflops": rec_flops / (rec_ms * 1e-3) / 1e12,
-            "rec_share": enc_ms / full_ms, "kernel_ms": {"encode": enc_ms, "encode+decode": full_ms}}
+def kernel_rooflines(prof, steps, chunks, beam, peak_hbm):
+    """Per-kernel achieved rates from the library's CUDA-event timings over the timed region.
+    Algorithmic work per chunk: see the constants at the top."""
+    out = {}
+    units = chunks * steps
+    # K3: recurrent LSTM (4 launches per wave: raw L0/L1, event L0/L1)
+    rec_ms = prof["recurrent_lstm"]["ms"]
+    rec_flop = units * (T_RAW + T_EV) * 2 * 2 * REC_FLOP_PER_STEP_ROW
+    rec_bytes = units * (T_RAW + T_EV) * 2 * (REC_BYTES_L0 + REC_BYTES_L1)
+    out["recurrent_lstm"] = {"ms": rec_ms, "launches": prof["recurrent_lstm"]["launches"],
+                             "gbs": rec_bytes / (rec_ms * 1e-3) / 1e9, "tflops": rec_flop / (rec_ms * 1e-3) / 1e12}
+    # K2: projection GEMMs of encoder layer 1 (raw + event): 524288 FLOP and (256 in + 1024 out) * 4 B per timestep
+    g_ms = prof["projection_gemm"]["ms"]
+    g_flop = units * (T_RAW + T_EV) * 524288.0
+    g_bytes = units * (T_RAW + T_EV) * (256 + 1024) * 4.0
+    out["projection_gemm"] = {"ms": g_ms, "launches": prof["projection_gemm"]["launches"],
+                              "gbs": g_bytes / (g_ms * 1e-3) / 1e9, "tflops": g_flop / (g_ms * 1e-3) / 1e12}
+    # K4+K5: decoder: values streamed once per decode step (folded query), 33 steps
+    d_ms = prof["decoder"]["ms"]
+    d_bytes = units * 33 * (T_RAW + T_EV) * 256 * 4.0
+    d_flop = units * 33 * beam * 546048.0
+    out["decoder"] = {"ms": d_ms, "launches": prof["decoder"]["launches"],
+                      "gbs": d_bytes / (d_ms * 1e-3) / 1e9, "tflops": d_flop / (d_ms * 1e-3) / 1e12}
+    for k in out:
+        out[k]["frac_hbm"] = out[k]["gbs"] / peak_hbm
+    return out
 
 
 def main():

@@ -161,8 +161,13 @@ int rvb_gather_tree(const int32_t *d_step_ids, const int32_t *d_parent_ids, cons
 int rvb_project(const float *d_a, const float *d_b, const float *d_bias, float *d_c,
                 int64_t m, int n, int k, int precision, void *stream);
 
-/* Introspection for bench.py: kernels launched by this library since load. */
+/* Introspection for bench.py: kernels launched by this library since load, and optional
+ * per-kernel device timing (CUDA events on the launching stream).  rvb_profile(1) starts a
+ * fresh recording, rvb_profile(0) stops; rvb_profile_read fills ms[5] / launches[5] in the order
+ * event scan, projection GEMM, recurrent LSTM, decoder, other (synchronises the device). */
 int64_t rvb_launch_count(void);
+int rvb_profile(int enable);
+int rvb_profile_read(double *ms, int64_t *launches, int n);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,8 @@ _PROTOS = {
     "rvb_last_error": (C.c_char_p, []),
     "rvb_device_count": (_i, [_p]),
     "rvb_launch_count": (_i64, []),
+    "rvb_profile": (_i, [_i]),
+    "rvb_profile_read": (_i, [_p, _p, _i]),
     "rvb_event_detect_workspace_bytes": (_i, [_p, C.c_int32, _p]),
     "rvb_event_detect": (_i, [_p, _i, _p, C.c_int32, _i, _i, _d, _d, _d, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "rvb_build_snippets": (_i, [_p, _i, _i64, _p, _p, _p, _p, C.c_int32, _i64, _i64, C.c_int32, _p, _p, C.c_int32, _p, _p]),
@@ -68,3 +70,17 @@ def device_count() -> int:
 
 def launch_count() -> int:
     return int(lib.rvb_launch_count())
+
+
+KERNEL_KINDS = ("event_scan", "projection_gemm", "recurrent_lstm", "decoder", "other")
+
+
+def profile(enable: bool) -> None:
+    check(lib.rvb_profile(1 if enable else 0))
+
+
+def profile_read() -> dict:
+    ms = (C.c_double * 5)()
+    n = (C.c_int64 * 5)()
+    check(lib.rvb_profile_read(ms, n, 5))
+    return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(KERNEL_KINDS)}

@@ -7,8 +7,28 @@
 
 #include "kernels.cuh"
 
+#include <mutex>
+
 namespace rvb {
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+
+struct ProfEntry { int kind; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfEntry> g_prof;
+
+void prof_record(int kind, cudaStream_t stream, bool begin) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (begin) {
+        ProfEntry e{kind, nullptr, nullptr};
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, stream);
+        g_prof.push_back(e);
+    } else {
+        for (auto it = g_prof.rbegin(); it != g_prof.rend(); ++it)
+            if (it->kind == kind) { cudaEventRecord(it->b, stream); break; }
+    }
+}
 
 // utils.input_mask (utils.py:26-32): mask[b,t] = all_f(x[b,t,f] != 0)
 __global__ void input_mask_kernel(const float *x, int F, long long B, int T, uint8_t *mask, int Tm, int t_off) {
@@ -455,6 +475,27 @@ extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, cons
         if (wave_steps > *h_steps) *h_steps = wave_steps;
     }
     return rvb_model_check(m);
+}
+
+// Per-kernel device time since rvb_profile(1): ms[k], launches[k] for k in KernelKind order
+// (event scan, projection GEMM, recurrent LSTM, decoder, other).  Synchronises the device.
+extern "C" int rvb_profile(int enable) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    g_prof.clear();
+    g_prof_on.store(enable ? 1 : 0);
+    return RVB_OK;
+}
+extern "C" int rvb_profile_read(double *ms, int64_t *launches, int n) {
+    if (!ms || !launches || n < KK_COUNT) return fail(RVB_ERR_ARG, "profile_read: need %d slots", (int)KK_COUNT);
+    RVB_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int k = 0; k < n; ++k) { ms[k] = 0.0; launches[k] = 0; }
+    for (auto &e : g_prof) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) { ms[e.kind] += t; launches[e.kind] += 1; }
+    }
+    return RVB_OK;
 }
 
 extern "C" int rvb_model_check(rvb_model_t *m) {

@@ -26,6 +26,18 @@ inline int fail(int code, const char *fmt, ...) {
 extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----
+enum KernelKind { KK_EVENT = 0, KK_GEMM = 1, KK_REC = 2, KK_DECODER = 3, KK_OTHER = 4, KK_COUNT = 5 };
+void prof_record(int kind, cudaStream_t stream, bool begin);
+extern std::atomic<int> g_prof_on;
+struct ProfScope {
+    int kind; cudaStream_t stream; bool on;
+    ProfScope(int k, cudaStream_t s) : kind(k), stream(s), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
+        if (on) prof_record(kind, stream, true);
+    }
+    ~ProfScope() { if (on) prof_record(kind, stream, false); }
+};
+
 #define RVB_CUDA(expr)                                                                       \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

@@ -417,7 +417,8 @@ int run(const Params &p, cudaStream_t stream) {
     RVB_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int SN = RMAX / p.W;
     dim3 grid((unsigned)((p.B + SN - 1) / SN));
-    decoder_kernel<<<grid, THREADS, smem, stream>>>(p);
+    { ProfScope ps(KK_DECODER, stream);
+      decoder_kernel<<<grid, THREADS, smem, stream>>>(p); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;

@@ -437,12 +437,14 @@ extern "C" int rvb_event_detect(const void *d_signal, int sample_bytes, const in
     p.chain = reinterpret_cast<ed::Chain *>(ws + L.chain);
     p.ticket = reinterpret_cast<int *>(ws + L.ticket);
     p.status = p.ticket + 1;
+    { ProfScope ps(KK_EVENT, stream);
     if (sample_bytes == 4) {
         RVB_CUDA(cudaFuncSetAttribute(ed::event_detect_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ed::SMEM_BYTES));
         ed::event_detect_kernel<int32_t><<<(unsigned)L.n_chunks, ed::THREADS, ed::SMEM_BYTES, stream>>>(p);
     } else {
         RVB_CUDA(cudaFuncSetAttribute(ed::event_detect_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ed::SMEM_BYTES));
         ed::event_detect_kernel<int16_t><<<(unsigned)L.n_chunks, ed::THREADS, ed::SMEM_BYTES, stream>>>(p);
+    }
     }
     RVB_LAUNCH_CHECK();
     count_launch();

@@ -181,7 +181,8 @@ static int launch(const Params &p, cudaStream_t stream) {
     RVB_CUDA(cudaFuncSetAttribute(lstm_rec_kernel<F, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int tiles = (p.B + BT - 1) / BT;
     dim3 grid((unsigned)(tiles * 2 * 2));
-    lstm_rec_kernel<F, PRE><<<grid, THREADS, smem, stream>>>(p);
+    { ProfScope ps(KK_REC, stream);
+      lstm_rec_kernel<F, PRE><<<grid, THREADS, smem, stream>>>(p); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;

@@ -85,7 +85,8 @@ int run_simt(const float *A, const float *Bm, const float *bias, float *C, long 
     if (M <= 0) return RVB_OK;
     if (N % TN != 0 || K % TK != 0) return fail(RVB_ERR_ARG, "gemm_simt: N %% 128 and K %% 16 must be 0 (N=%d K=%d)", N, K);
     dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)(N / TN));
-    gemm_simt_kernel<<<grid, THREADS, 0, stream>>>(A, Bm, bias, C, M, N, K);
+    { ProfScope ps(KK_GEMM, stream);
+      gemm_simt_kernel<<<grid, THREADS, 0, stream>>>(A, Bm, bias, C, M, N, K); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;

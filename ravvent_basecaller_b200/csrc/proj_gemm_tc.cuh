@@ -290,7 +290,8 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
     const long long tiles = (long long)(N / BN) * ((M + BM - 1) / BM);
     if (tiles > 0x7fffffffLL) return fail(RVB_ERR_ARG, "projection too large for one launch");
     dim3 grid((unsigned)tiles);
-    gemm_tc_kernel<BN, NPASS><<<grid, THREADS, cfg::SMEM, stream>>>(ma, mh, ml, bias, C, M, N, K, abort_flag);
+    { ProfScope ps(KK_GEMM, stream);
+      gemm_tc_kernel<BN, NPASS><<<grid, THREADS, cfg::SMEM, stream>>>(ma, mh, ml, bias, C, M, N, K, abort_flag); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;

@@ -54,3 +54,37 @@ def calc_prob_logits_beam_search_scores(beam_scores):
     prev = np.zeros_like(s)
     prev[..., 1:] = s[..., :-1]
     return np.exp(s - prev)
+
+
+def load_data_from_signal(raw, label_start=None, label_end=None, stride=6, device=None, detector=None):
+    """Inference half of ``load_data_from_single_signal_label`` (data_loader.py:113-126) for one read that
+    is already in memory: GPU event detection (K1), then the GPU snippet builder.
+
+    raw: 1-D integer samples.  ``label_start`` / ``label_end`` are the first start / last end of the
+    labelled sample range (``nuc_raw_ranges[0,0]`` / ``nuc_raw_ranges[-1,1]``); default: the whole read.
+    -> (raw_snippets [Ns,200,1] f32, event_snippets [Ns,30,5] f32) torch tensors on the device."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from .event_detector import EventDetector
+    arr = np.asarray(raw)
+    n = int(arr.size)
+    det = detector or EventDetector(ED_WINDOW_LENGTH_1, ED_WINDOW_LENGTH_2, device=device)
+    dev = det.device
+    if arr.dtype != np.int16:
+        arr = arr.astype(np.int32)
+    sig = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    ev = det.detect_batch(sig, [0, n])
+    n_ev = int(ev["count"][0].item()) if n else 0
+    lab0 = 0 if label_start is None else int(label_start)
+    lab1 = n if label_end is None else int(label_end)
+    cap = max(1, (n_ev + int(stride) - 1) // int(stride))
+    with torch.cuda.device(dev):
+        raw_s = torch.zeros((cap, MAX_RAW_LEN, 1), dtype=torch.float32, device=dev)
+        ev_s = torch.zeros((cap, MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
+        cnt = C.c_int32(0)
+        _lib.check(_lib.lib.rvb_build_snippets(
+            sig.data_ptr(), sig.element_size(), n, ev["start"].data_ptr(), ev["length"].data_ptr(),
+            ev["mean"].data_ptr(), ev["stdv"].data_ptr(), n_ev, lab0, lab1, int(stride),
+            raw_s.data_ptr(), ev_s.data_ptr(), cap, C.byref(cnt), torch.cuda.current_stream(dev).cuda_stream))
+    return raw_s[:cnt.value], ev_s[:cnt.value]

@@ -1,0 +1,57 @@
+"""GPU snippet builder (K1 -> rvb_build_snippets) against the reference's prepare_snippets output
+(golden fixtures) and the oracle.  Window counts / padding pattern exact; values within 1 float32 ulp
+(sklearn accumulates the scaler moments in a different order)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import event_ref, snippet_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _ulp_close(a, b, ulps=1):
+    return np.all(np.abs(a - b) <= ulps * np.spacing(np.maximum(np.abs(a), np.abs(b)).astype(np.float32)))
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_matches_reference_golden(k):
+    from ravvent_basecaller_b200 import data_loader as dl
+    g = np.load(GOLDEN / "snippets_golden.npz")
+    raw = g[f"raw_{k}"].astype(np.int32)
+    lab0, lab1, stride = (int(v) for v in g[f"par_{k}"])
+    rs, es = dl.load_data_from_signal(raw, lab0, lab1, stride)
+    rs, es = rs.cpu().numpy(), es.cpu().numpy()
+    assert rs.shape == g[f"raw_snips_{k}"].shape and es.shape == g[f"event_snips_{k}"].shape
+    assert np.array_equal(rs == 0, g[f"raw_snips_{k}"] == 0)
+    assert np.array_equal(es == 0, g[f"event_snips_{k}"] == 0)
+    assert _ulp_close(rs, g[f"raw_snips_{k}"]) and _ulp_close(es, g[f"event_snips_{k}"])
+
+
+def test_against_oracle_on_a_full_read_and_feeds_the_event_model():
+    """BASELINE configs[1]: GPU event detection feeding the event encoder, beam 1."""
+    import ravvent_basecaller_b200 as rb
+    from ravvent_basecaller_b200 import data_loader as dl
+    from oracle import model_ref as mr
+    raw = event_ref.synth_read(np.random.default_rng(42), 60000)
+    rs, es = dl.load_data_from_signal(raw, stride=6)
+    ev = event_ref.detect_events(raw, 6, 9)
+    ref = snippet_ref.build_snippets(raw, ev.start, ev.length, ev.mean, ev.stdv, 0, raw.size, 6)
+    assert rs.shape == ref["raw"].shape and es.shape == ref["event"].shape and rs.shape[0] > 900
+    assert _ulp_close(rs.cpu().numpy(), ref["raw"]) and _ulp_close(es.cpu().numpy(), ref["event"])
+    w = mr.init_weights(22)
+    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, 'event', 0.)
+    bc.load_weights(w)
+    ids, sc = bc.beam_search_prediction(es[:64], 1, 12)
+    enc, mask = mr.encode_input(w, ref["event"][:64], "event")
+    rid, rsc = mr.beam_search(w, enc, mask, 1, 12)
+    same = np.array([np.array_equal(a, b) for a, b in zip(ids.cpu().numpy(), rid)])
+    assert same.mean() >= 0.95
+
+
+def test_short_and_empty_reads():
+    from ravvent_basecaller_b200 import data_loader as dl
+    for n in (0, 10, 150):
+        raw = event_ref.synth_read(np.random.default_rng(n), n) if n else np.zeros(0, np.int32)
+        rs, es = dl.load_data_from_signal(raw)
+        assert rs.shape[0] == 0 and es.shape[0] == 0
