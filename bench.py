@@ -139,7 +139,7 @@ def run_reference(args, rank, world):
     cores = os.cpu_count()
     line = {
         "impl": "reference", "metric": "read-equivalent bases/sec (joint model, beam%d)" % args.beam, "value": v,
-        "unit": "bases/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "joint raw+event model, beam%d, S=33, %d-chunk sample of the synthetic chunk set, "
                                "predict batch 1024" % (args.beam, n)},

@@ -25,6 +25,7 @@ SOURCES = {
     "api.cu": [],
     "event_detect.cu": ["-fmad=false"],
     "lstm_recurrent.cu": [],
+    "lstm_recurrent_tc.cu": [],
     "proj_gemm.cu": [],
     "decoder.cu": [],
     "snippets.cu": ["-fmad=false"],

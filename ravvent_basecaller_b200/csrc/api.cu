@@ -61,6 +61,9 @@ struct rvb_model {
     float *d_phi[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // tf32 hi part, [N,K]
     float *d_plo[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // remainder, [N,K]
     int *d_abort = nullptr;
+    bool rec_tc = false;                       // recurrences on tcgen05 (lstm_recurrent_tc.cu)
+    uint16_t *d_bimg[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    float *d_w0[2] = {nullptr, nullptr};
     float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
     // workspace for one wave
     size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
@@ -131,6 +134,8 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     if (wave_snippets > 0) m->wave = (wave_snippets + 63) / 64 * 64;
     const char *g = getenv("RVB_GEMM");
     m->use_tc = gemm::tc_available() && !(g && strcmp(g, "simt") == 0);
+    const char *r = getenv("RVB_REC");
+    m->rec_tc = m->use_tc && !(r && strcmp(r, "ffma") == 0);
     *out = m;
     return RVB_OK;
 }
@@ -186,6 +191,8 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
             std::vector<float> pack((size_t)2 * 2 * KX * 256);
             std::vector<float> wcat, bcat;
             if (l > 0) { wcat.resize((size_t)ENC_OUT * 2 * GATES); bcat.resize(2 * GATES); }
+            std::vector<uint16_t> bimg(m->rec_tc ? (size_t)4 * (rectc::B_IMAGE_BYTES / 2) : 0);
+            std::vector<float> w0(m->rec_tc && l == 0 ? (size_t)2 * rectc::W0_FLOATS_PER_DIR : 0, 0.0f);
             for (int d = 0; d < 2; ++d) {
                 std::string base = std::string(enc_name[e]) + "/layer" + std::to_string(l) + "/" + dir_name[d] + "/";
                 const HostTensor *W, *U, *Bv;
@@ -204,12 +211,32 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
                                 pack[(((size_t)(d * 2 + r) * KX + k) * 4 + g) * 64 + u] = v;
                             }
                 if (l > 0) {
+                    // gate columns: Keras order (gate*128 + unit) for the FFMA recurrence, unit-major (unit*4 + gate)
+                    // for the tensor-core recurrence whose TMEM columns are laid out that way
                     for (int k = 0; k < ENC_OUT; ++k)
-                        for (int n = 0; n < GATES; ++n) wcat[(size_t)k * 2 * GATES + d * GATES + n] = W->data[(size_t)k * GATES + n];
-                    for (int n = 0; n < GATES; ++n) bcat[d * GATES + n] = Bv->data[n];
+                        for (int n = 0; n < GATES; ++n) {
+                            const int col = m->rec_tc ? (n % UNITS) * 4 + n / UNITS : n;
+                            wcat[(size_t)k * 2 * GATES + d * GATES + col] = W->data[(size_t)k * GATES + n];
+                        }
+                    for (int n = 0; n < GATES; ++n) bcat[d * GATES + (m->rec_tc ? (n % UNITS) * 4 + n / UNITS : n)] = Bv->data[n];
+                }
+                if (m->rec_tc) {
+                    for (int r = 0; r < 2; ++r)
+                        rectc::pack_b_image(U->data.data(), r, bimg.data() + (size_t)(d * 2 + r) * (rectc::B_IMAGE_BYTES / 2));
+                    if (l == 0) {
+                        for (int f = 0; f <= F; ++f)
+                            for (int n = 0; n < GATES; ++n)
+                                w0[(size_t)d * rectc::W0_FLOATS_PER_DIR + (size_t)f * GATES + (n % UNITS) * 4 + n / UNITS] =
+                                    f < F ? W->data[(size_t)f * GATES + n] : Bv->data[n];
+                    }
                 }
             }
             RVB_CHECK(upload(m, &m->d_rec[e][l], pack));
+            if (m->rec_tc) {
+                RVB_CHECK(dmalloc(m, &m->d_bimg[e][l], bimg.size()));
+                RVB_CUDA(cudaMemcpy(m->d_bimg[e][l], bimg.data(), bimg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+                if (l == 0) RVB_CHECK(upload(m, &m->d_w0[e], w0));
+            }
             if (l > 0) {
                 RVB_CHECK(upload(m, &m->d_pw[e][l], wcat));
                 RVB_CHECK(upload(m, &m->d_pb[e][l], bcat));
@@ -301,7 +328,23 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
     const int feat = e == 0 ? 1 : 5;
     float **yb = e == 0 ? m->y_raw : m->y_ev;
     float *G = e == 0 ? m->G_raw : m->G_ev;
-    for (int l = 0; l < m->enc_depth; ++l) {
+    for (int l = 0; l < m->enc_depth && m->rec_tc; ++l) {
+        // tensor-core recurrence; intermediates are time-major (row = t*nb + b) so that a tile's rows of one
+        // timestep are contiguous for both K2 and K3
+        const bool last = (l == m->enc_depth - 1);
+        rectc::Params p{};
+        p.x = x; p.G = G; p.g_bs = 2 * GATES; p.g_ts = (long long)nb * 2 * GATES;
+        p.bimg = m->d_bimg[e][l]; p.w0 = m->d_w0[e];
+        p.state_in = l == 0 ? nullptr : m->st[e][(l - 1) & 1];
+        p.state_out = m->st[e][l & 1];
+        p.y = last ? out + (size_t)t_off * ENC_OUT : yb[l & 1];
+        p.y_bs = last ? (long long)Tm * ENC_OUT : ENC_OUT;
+        p.y_ts = last ? ENC_OUT : (long long)nb * ENC_OUT;
+        p.B = nb; p.T = T; p.abort_flag = m->d_abort;
+        if (l > 0) RVB_CHECK(project(m, e, l, yb[(l - 1) & 1], G, (long long)nb * T, s));
+        RVB_CHECK(rectc::run(l == 0 ? feat : 0, p, s));
+    }
+    for (int l = 0; l < m->enc_depth && !m->rec_tc; ++l) {
         const bool last = (l == m->enc_depth - 1);
         rec::Params p{};
         p.x = x; p.G = G; p.wpack = m->d_rec[e][l];

@@ -19,6 +19,26 @@ int run(int feat, const Params &p, cudaStream_t stream);
 int kx_rows(int feat);
 }  // namespace rec
 
+namespace rectc {   // K3 on tcgen05 (cta_group::2), lstm_recurrent_tc.cu
+struct Params {
+    const float *x;             // [B,T,F] batch-major (layer 0)
+    const float *G;             // pre-gates (layer > 0): element (b,t,dir*512 + unit*4 + gate) at G[b*g_bs + t*g_ts + ...]
+    long long g_bs, g_ts;
+    const uint16_t *bimg;       // [dir][rank] pre-swizzled fp16 hi/lo B-operand images (pack_b_image)
+    const float *w0;            // [dir][6][512] layer-0 input rows + bias row, [unit][gate] column order
+    const float *state_in;      // [B,2,2,128] or nullptr
+    float *state_out;
+    float *y;                   // (b,t,dir*128+u) at y[b*y_bs + t*y_ts + dir*128 + u]
+    long long y_bs, y_ts;
+    int B, T;
+    int *abort_flag;
+};
+int run(int feat, const Params &p, cudaStream_t stream);
+void pack_b_image(const float *U, int rank, uint16_t *img);
+constexpr int B_IMAGE_BYTES = 8 * 16384;
+constexpr int W0_FLOATS_PER_DIR = 6 * 512;
+}  // namespace rectc
+
 namespace gemm {    // K2, proj_gemm.cu
 int run_simt(const float *A, const float *Bm, const float *bias, float *C, long long M, int N, int K, cudaStream_t s);
 // tcgen05 path: WhiT / WloT are the [N,K] tf32 hi / remainder parts made by prepare_weights

@@ -1,0 +1,356 @@
+// K3 on tensor cores -- persistent recurrent LSTM with tcgen05.mma cta_group::2, fp32-level accuracy.
+//
+// Replaces the Keras RNN(LSTMCell) while-loop of Encoder.call (reference basecaller.py:19-32, 48-59).
+//
+// A thread-block cluster of two CTAs handles (256 snippets, one direction): each CTA owns 128 batch rows
+// and their full 512 gate columns as fp32 accumulators in its own TMEM (128 lanes x 512 columns = all of
+// it).  The recurrent kernel U is the B operand of the pair: each CTA keeps HALF of the gate columns
+// resident in shared memory for all T steps, as fp16 hi + fp16 lo (U = U_hi + U_lo, 64 KB + 64 KB), and the
+// 2-SM MMA reads both halves -- no per-step weight traffic and no DSMEM exchange of h.
+// Split precision: h = h_hi + h_lo (fp16 each); per step and per 256-column half the leader CTA issues
+//     D  = h_lo.U_hi + h_hi.U_lo + h_hi.U_hi          (3 x 8 MMAs of M256 N256 K16, kind::f16, fp32 accumulate)
+// which drops only the lo.lo term (~2^-22 relative): the recurrence keeps fp32-parity accuracy on the
+// fp16 pipe.  Eight epilogue warps (TMEM lane quarter = warp % 4, column half = warp / 4) read the
+// accumulators with tcgen05.ld, add the input contribution (layer 0: x_t.W + b from shared memory;
+// layers > 0: the pre-projected gates written by K2), apply the fused gate nonlinearities / cell update
+// (c stays in registers), write y to HBM and store the next h as fp16 hi/lo straight into the
+// 128-byte-swizzled K-major A-operand tiles.  Per step: one cluster-scope mbarrier (h ready -> MMA) and
+// one multicast tcgen05.commit (accumulators ready -> both CTAs' epilogues).  Waits are bounded.
+#include <cuda_fp16.h>
+
+#include "kernels.cuh"
+
+namespace rvb {
+namespace rectc {
+
+constexpr int THREADS = 320;          // w0 spare, w1 TMEM alloc + MMA issue, w2..w9 epilogue
+constexpr int ROWS = 128;             // batch rows per CTA
+constexpr int TILE_BYTES = 16384;     // [128 rows][64 fp16] K-major SW128 tile
+constexpr int A_BYTES = 4 * TILE_BYTES;     // (hi|lo) x (kb 0|1)
+constexpr int B_BYTES = 8 * TILE_BYTES;     // (half j) x (hi|lo) x (kb)
+constexpr int W0_FLOATS = 6 * GATES;        // layer 0: up to 5 feature rows + bias, [unit][gate] order
+constexpr size_t SMEM = 1024 + A_BYTES + B_BYTES + W0_FLOATS * 4 + 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 2.0f * fsig(2.0f * x) - 1.0f; }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, int *abort_flag) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return true;
+        if ((it & 1023u) == 1023u && *reinterpret_cast<volatile int *>(abort_flag) != 0) return false;
+    }
+    atomicExch(abort_flag, 1);
+    return false;
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {          // K-major SW128, SBO = 1024 B
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16, A = B = fp16 (format 0), D = fp32, K-major both, M = 256 (pair), N = 256
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+// Store 8 consecutive units of h (k = 64*kb + 8*chunk .. +7) of `row` as fp16 hi and lo into the A tiles.
+__device__ __forceinline__ void store_h8(unsigned char *a_tiles, int row, int kb, int chunk, const float (&h)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half h0 = __float2half_rn(h[2 * i]), h1 = __float2half_rn(h[2 * i + 1]);
+        const __half l0 = __float2half_rn(h[2 * i] - __half2float(h0)), l1 = __float2half_rn(h[2 * i + 1] - __half2float(h1));
+        hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const int off = kb * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4 *>(a_tiles + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(a_tiles + 2 * TILE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+template <int F, bool PRE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec_tc_kernel(Params p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char *a_tiles = smem;                                   // [hi kb0][hi kb1][lo kb0][lo kb1]
+    unsigned char *b_tiles = smem + A_BYTES;                         // [(j*2 + part)*2 + kb]
+    float *w0s = reinterpret_cast<float *>(smem + A_BYTES + B_BYTES);   // [(F + 1)][512] layer-0 input rows + bias
+    uint64_t *h_ready = reinterpret_cast<uint64_t *>(smem + A_BYTES + B_BYTES + W0_FLOATS * 4);
+    uint64_t *acc_full = h_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 2);
+
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cid = blockIdx.x >> 1;
+    const int dir = cid & 1;
+    const int b0 = (cid >> 1) * (2 * ROWS) + (int)rank * ROWS;
+    const int T = p.T, B = p.B;
+
+    // ---- one-time setup: resident B operand (pre-swizzled image), layer-0 rows, barriers, TMEM ----------
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.bimg + (size_t)(dir * 2 + rank) * (B_BYTES / 2));   // bimg counts uint16
+        uint4 *dst = reinterpret_cast<uint4 *>(b_tiles);
+        for (int i = threadIdx.x; i < B_BYTES / 16; i += THREADS) dst[i] = __ldg(src + i);
+        if (!PRE)
+            for (int i = threadIdx.x; i < (F + 1) * GATES; i += THREADS) w0s[i] = __ldg(p.w0 + (size_t)dir * W0_FLOATS + i);
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(h_ready, 16);          // 8 epilogue warps x 2 CTAs (only the leader CTA's copy is used)
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+
+    if (warp == 1) {
+        // ================= MMA issuer: one thread of the leader CTA drives both SMs =================
+        if (rank == 0 && lane == 0) {
+            const uint32_t a0 = smem_u32(a_tiles), bb = smem_u32(b_tiles);
+            for (int s = 0; s < T; ++s) {
+                if (!mbar_wait_cluster(h_ready, s & 1, p.abort_flag)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint32_t d = tmem_base + (uint32_t)(j * 256);
+#pragma unroll
+                    for (int combo = 0; combo < 3; ++combo) {
+                        const int pa = (combo == 0) ? 1 : 0;      // h_lo.U_hi, h_hi.U_lo, h_hi.U_hi
+                        const int pb = (combo == 1) ? 1 : 0;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = make_desc(a0 + (pa * 2 + kb) * TILE_BYTES + ks * 32);
+                                const uint64_t bd = make_desc(bb + ((j * 2 + pb) * 2 + kb) * TILE_BYTES + ks * 32);
+                                umma_f16_2sm(d, ad, bd, (combo | kb | ks) ? 1u : 0u);
+                            }
+                    }
+                }
+                umma_commit_2sm(acc_full);
+            }
+        }
+    } else if (warp >= 2) {
+        // ================= epilogue warps: gates, cell update, next h ================================
+        const int q = warp & 3, hlf = (warp - 2) >> 2;
+        const int row = 32 * q + lane;
+        const int b = b0 + row;
+        const bool live = b < B;
+        float c[64];
+        {
+            float h0[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) { c[i] = 0.0f; h0[i] = 0.0f; }
+            if (p.state_in != nullptr && live) {
+                const float *si = p.state_in + (((size_t)b * 2 + dir) * 2) * UNITS + 64 * hlf;
+#pragma unroll
+                for (int i = 0; i < 64; i += 4) {
+                    const float4 hv = *reinterpret_cast<const float4 *>(si + i);
+                    const float4 cv = *reinterpret_cast<const float4 *>(si + UNITS + i);
+                    h0[i] = hv.x; h0[i + 1] = hv.y; h0[i + 2] = hv.z; h0[i + 3] = hv.w;
+                    c[i] = cv.x; c[i + 1] = cv.y; c[i + 2] = cv.z; c[i + 3] = cv.w;
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float h8[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) h8[u] = h0[8 * ch + u];
+                store_h8(a_tiles, row, hlf, ch, h8);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(h_ready, 0);
+
+        bool ok = true;
+        float *so = (p.state_out != nullptr && live) ? p.state_out + (((size_t)b * 2 + dir) * 2) * UNITS + 64 * hlf : nullptr;
+        for (int s = 0; s < T && ok; ++s) {
+            const int t = dir ? T - 1 - s : s;
+            float xin[F];
+            if (!PRE) {
+#pragma unroll
+                for (int f = 0; f < F; ++f) xin[f] = live ? __ldg(p.x + ((size_t)b * T + t) * F + f) : 0.0f;
+            }
+            const float *grow = PRE ? p.G + (size_t)b * p.g_bs + (size_t)t * p.g_ts + dir * GATES + 256 * hlf : nullptr;
+            float *yrow = p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf;
+            ok = mbar_wait_cluster(acc_full, s & 1, p.abort_flag);
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                float h8[8];
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int col = 32 * ch + 16 * sub;          // within this warp's 256-column half
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 * hlf + col), r);
+                    float z[16];
+                    if (PRE) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 g = live ? __ldg(reinterpret_cast<const float4 *>(grow + col + i)) : make_float4(0, 0, 0, 0);
+                            z[i] = g.x; z[i + 1] = g.y; z[i + 2] = g.z; z[i + 3] = g.w;
+                        }
+                    } else {
+                        const float *wr = w0s + 256 * hlf + col;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            float4 a = *reinterpret_cast<const float4 *>(wr + F * GATES + i);          // bias row
+#pragma unroll
+                            for (int f = 0; f < F; ++f) {
+                                const float4 w = *reinterpret_cast<const float4 *>(wr + f * GATES + i);
+                                a.x = fmaf(xin[f], w.x, a.x); a.y = fmaf(xin[f], w.y, a.y);
+                                a.z = fmaf(xin[f], w.z, a.z); a.w = fmaf(xin[f], w.w, a.w);
+                            }
+                            z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
+                        }
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float zi = z[4 * u + 0] + __uint_as_float(r[4 * u + 0]);
+                        const float zf = z[4 * u + 1] + __uint_as_float(r[4 * u + 1]);
+                        const float zg = z[4 * u + 2] + __uint_as_float(r[4 * u + 2]);
+                        const float zo = z[4 * u + 3] + __uint_as_float(r[4 * u + 3]);
+                        const int ci = 8 * ch + 4 * sub + u;
+                        const float cn = fsig(zf) * c[ci] + fsig(zi) * ftanh(zg);
+                        c[ci] = cn;
+                        h8[4 * sub + u] = fsig(zo) * ftanh(cn);
+                    }
+                }
+                store_h8(a_tiles, row, hlf, ch, h8);
+                if (live) {
+                    *reinterpret_cast<float4 *>(yrow + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
+                    *reinterpret_cast<float4 *>(yrow + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);
+                    if (so != nullptr && s == T - 1) {
+                        *reinterpret_cast<float4 *>(so + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
+                        *reinterpret_cast<float4 *>(so + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && s + 1 < T) mbar_arrive_remote(h_ready, 0);
+        }
+        if (so != nullptr && ok) {
+#pragma unroll
+            for (int i = 0; i < 64; i += 4)
+                *reinterpret_cast<float4 *>(so + UNITS + i) = make_float4(c[i], c[i + 1], c[i + 2], c[i + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int F, bool PRE>
+static int launch(const Params &p, cudaStream_t stream) {
+    RVB_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<F, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    const int clusters = (p.B + 2 * ROWS - 1) / (2 * ROWS) * 2;          // x 2 directions
+    {
+        ProfScope ps(KK_REC, stream);
+        lstm_rec_tc_kernel<F, PRE><<<dim3((unsigned)(clusters * 2)), THREADS, SMEM, stream>>>(p);
+    }
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+
+int run(int feat, const Params &p, cudaStream_t stream) {
+    if (p.B <= 0 || p.T <= 0) return RVB_OK;
+    if (feat == 1) return launch<1, false>(p, stream);
+    if (feat == 5) return launch<5, false>(p, stream);
+    if (feat == 0) return launch<1, true>(p, stream);
+    return fail(RVB_ERR_ARG, "lstm_rec_tc: unsupported feature count %d", feat);
+}
+
+// ---- host-side packing ---------------------------------------------------------------------------------
+// B-operand image for (dir, rank): tiles [(j*2 + part)*2 + kb] of [128 N-rows][64 K] fp16, K-major SW128.
+// N row n of half j in CTA `rank` is gate column  n_global = j*256 + rank*128 + n = unit*4 + gate.
+void pack_b_image(const float *U /*[128][512] Keras order*/, int rank, uint16_t *img /*B_BYTES/2*/) {
+    for (int j = 0; j < 2; ++j)
+        for (int part = 0; part < 2; ++part)
+            for (int kb = 0; kb < 2; ++kb)
+                for (int n = 0; n < 128; ++n)
+                    for (int k = 0; k < 64; ++k) {
+                        const int ng = j * 256 + rank * 128 + n;
+                        const int unit = ng >> 2, gate = ng & 3;
+                        const float v = U[(size_t)(kb * 64 + k) * GATES + gate * UNITS + unit];
+                        const __half hi = __float2half_rn(v);
+                        const __half lo = __float2half_rn(v - __half2float(hi));
+                        const size_t off = (size_t)((j * 2 + part) * 2 + kb) * TILE_BYTES + (n >> 3) * 1024 + (n & 7) * 128 +
+                                           (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2;
+                        img[off / 2] = __half_as_ushort(part == 0 ? hi : lo);
+                    }
+}
+
+}  // namespace rectc
+}  // namespace rvb
