@@ -279,6 +279,7 @@ def run_ours(args, rank, local_rank, world):
                                  "FP32 peak), so this kernel is FP32-issue bound, not HBM bound; achieved = algorithmic "
                                  "bytes (DESIGN.md §5) / CUDA-event time"},
             "kernels": kr,
+            "event_path": event_path_bench(local_rank) if not args.no_event_path else None,
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -315,6 +316,69 @@ def kernel_rooflines(prof, steps, chunks, beam, peak_hbm):
     return out
 
 
+def event_path_bench(local_rank, n_reads=256, read_len=60000, iters=5):
+    """K1 (event scan) + snippet builder on synthetic reads: samples/s and achieved HBM GB/s
+    (algorithmic 6.5 B/sample), plus the C oracle on one read as the CPU figure."""
+    import ctypes
+    import torch
+    import ravvent_basecaller_b200 as rb
+    from ravvent_basecaller_b200 import _lib
+    rng = np.random.default_rng(77)
+    one = []
+    for _ in range(8):          # 8 distinct reads tiled to n_reads (generation is the slow part on the host)
+        n_lvl = read_len // 3 + 8
+        dwell = 2 + rng.geometric(1.0 / 7.0, size=n_lvl)
+        level = rng.uniform(250.0, 550.0, size=n_lvl)
+        sig = np.repeat(level, dwell)[:read_len] + rng.normal(0.0, 8.0, size=read_len)
+        one.append(np.rint(sig).astype(np.int32))
+    sig = np.concatenate([one[i % 8] for i in range(n_reads)])
+    offs = np.arange(n_reads + 1, dtype=np.int64) * read_len
+    dev = torch.device("cuda", local_rank)
+    det = rb.EventDetector(6, 9, device=local_rank)
+    d_sig = torch.from_numpy(sig).to(dev)
+    out = det.detect_batch(d_sig, offs)                       # warm-up
+    n_events = int(out["count"].sum().item())
+    _lib.profile(True)
+    for _ in range(iters):
+        det.detect_batch(d_sig, offs)
+    prof = _lib.profile_read(); _lib.profile(False)
+    ms = prof["event_scan"]["ms"] / max(1, prof["event_scan"]["launches"])
+    samples = n_reads * read_len
+    bytes_alg = samples * 4 + n_events * 24
+    peak, _ = measured_peaks()
+    res = {"reads": n_reads, "samples": samples, "events": n_events, "ms_per_launch": ms,
+           "samples_per_s": samples / (ms * 1e-3), "gbs": bytes_alg / (ms * 1e-3) / 1e9,
+           "frac_hbm": bytes_alg / (ms * 1e-3) / 1e9 / peak,
+           "note": "bit-exact float64 t-statistics make this kernel FP64-ALU bound, not HBM bound"}
+    # snippet builder on one read (per-read API), wall-clock incl. its stream sync
+    raw0 = one[0]
+    rb.data_loader.load_data_from_signal(raw0, stride=6, detector=det)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        rs, es = rb.data_loader.load_data_from_signal(raw0, stride=6, detector=det)
+    torch.cuda.synchronize(dev)
+    res["read_to_snippets_ms"] = (time.perf_counter() - t0) / 10 * 1e3
+    res["snippets_per_read"] = int(rs.shape[0])
+    # CPU: C restatement of the reference's per-sample loop, one core, one read
+    try:
+        subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle")])
+        lib = ctypes.CDLL(str(ROOT / "oracle" / "libravvent_oracle.so"))
+        lib.rvo_detect_events.restype = ctypes.c_int64
+        cap = read_len // 2 + 4
+        st = np.empty(cap, np.int32); ln = np.empty(cap, np.int32); mu = np.empty(cap, np.float64); sd = np.empty(cap, np.float64)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            lib.rvo_detect_events(ctypes.c_void_p(raw0.ctypes.data), ctypes.c_int64(read_len), 6, 9, ctypes.c_double(1.4),
+                                  ctypes.c_double(9.0), ctypes.c_double(0.2), ctypes.c_void_p(st.ctypes.data),
+                                  ctypes.c_void_p(ln.ctypes.data), ctypes.c_void_p(mu.ctypes.data), ctypes.c_void_p(sd.ctypes.data),
+                                  ctypes.c_int64(cap))
+        res["cpu_c_port_samples_per_s_1core"] = 20 * read_len / (time.perf_counter() - t0)
+    except Exception as e:                                     # the CPU figure is optional
+        res["cpu_c_port_samples_per_s_1core"] = None
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,6 +390,7 @@ def main():
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-event-path", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -179,7 +179,8 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
     int *raw_s = reinterpret_cast<int *>(sub_end + NSUB);
     int *fire_n = raw_s + RAW_CAP;            // accepted fires: n relative to chunk start a (1..CH)
     uint32_t *sub_mask = reinterpret_cast<uint32_t *>(fire_n + CH);
-    __shared__ int s_chunk, s_nfire, s_count0, s_abort;
+    __shared__ int s_chunk, s_nfire, s_count0, s_abort, s_inner_bad, s_parallel_emit;
+    __shared__ int sub_pre[NSUB];
     __shared__ uint32_t s_evst0;
     __shared__ long long s_mst0;
 
@@ -259,6 +260,20 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
     __syncthreads();
 
     // ---- phase C: exact verification against the true incoming state, chain to next chunk ----
+    // Chain-independent part first, in parallel: sub-segment q is consistent with q-1 if the speculative
+    // end state of q-1 equals the speculative start state of q.  If that holds for every q >= 1, the whole
+    // chunk is accepted as soon as the TRUE incoming state equals sub_start[0]: the chain-critical path is
+    // one compare + publish.  Anything else (first chunk of a read with its warm-up quirks, a mismatch,
+    // w1 > w2) takes the exact sequential walk below.
+    if (tid == 0) s_inner_bad = 0;
+    __syncthreads();
+    if (tid < nsub) {
+        if (tid >= 1 && !pair_equal(sub_end[tid - 1], sub_start[tid])) atomicOr(&s_inner_bad, 1);
+        int pre = 0;
+        for (int q = 0; q < tid; ++q) pre += __popc(sub_mask[q]);
+        sub_pre[tid] = pre;
+    }
+    __syncthreads();
     if (tid == 0) {
         Pair cur; uint32_t ev_st = 0; long long m_st = 0; int count = 0;
         if (ci == 0) { det_reset(cur.s); det_reset(cur.l); pair_normalise(cur, 0, w2); }
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(&prev->flag));
                 if (f != 0) break;
                 if (++spins > (1u << 24)) { ok = false; break; }
-                __nanosleep(100);
+                __nanosleep(40);
             }
             if (!ok) { atomicExch(p.status, RVB_ERR_INTERNAL); s_abort = 1; }
             const Chain *pc = p.chain + (c - 1);
@@ -278,27 +293,44 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
         }
         s_evst0 = ev_st; s_mst0 = m_st; s_count0 = count;
         int nfire = 0;
-        for (int q = 0; q < nsub; ++q) {
-            long long seg0 = a + (long long)q * SUB, seg1 = min(b, seg0 + SUB);
-            uint32_t mask;
-            if (pair_equal(cur, sub_start[q])) { mask = sub_mask[q]; cur = sub_end[q]; }
-            else {
-                mask = 0;
-                for (long long n = seg0 + 1; n <= seg1; ++n) {
-                    int j = (int)(n - ts_n0 - 1);
-                    if (pair_step(cur, ts1[j], ts2[j], (uint32_t)(n - w2), p)) mask |= 1u << (int)(n - seg0 - 1);
-                }
-                pair_normalise(cur, seg1, w2);
+        bool fast = (ci > 0) && fast_ok && !s_inner_bad && a >= (long long)buf && pair_equal(cur, sub_start[0]);
+        if (fast) {
+            const int total = sub_pre[nsub - 1] + __popc(sub_mask[nsub - 1]);
+            if (total > 0) {
+                int qf = 0; while (sub_mask[qf] == 0) ++qf;
+                int ql = nsub - 1; while (sub_mask[ql] == 0) --ql;
+                const long long n_first = a + (long long)qf * SUB + __ffs(sub_mask[qf]);
+                const long long n_last = a + (long long)ql * SUB + (32 - __clz(sub_mask[ql]));
+                const uint32_t en_first = (uint32_t)(n_first - w2) - (uint32_t)w1 + 1u;
+                if ((long long)en_first - (long long)ev_st < 1) fast = false;      // would be rejected (:194-195)
+                else { ev_st = (uint32_t)(n_last - w2) - (uint32_t)w1 + 1u; m_st = (long long)ev_st; }
             }
-            while (mask) {
-                int bit = __ffs(mask) - 1; mask &= mask - 1;
-                long long n = seg0 + 1 + bit;
-                uint32_t en = (uint32_t)(n - w2) - (uint32_t)w1 + 1u;       // event_detector.py:102-104
-                long long len = (long long)en - (long long)ev_st;
-                if (len < 1) continue;                                      // :194-195
-                fire_n[nfire++] = (int)(n - a);
-                ev_st = en; m_st = ring_latest(n, en % (uint32_t)buf, buf);
-                if (m_st < 0) m_st = -1;
+            if (fast) { cur = sub_end[nsub - 1]; nfire = total; }
+        }
+        s_parallel_emit = fast ? 1 : 0;
+        if (!fast) {
+            for (int q = 0; q < nsub; ++q) {
+                long long seg0 = a + (long long)q * SUB, seg1 = min(b, seg0 + SUB);
+                uint32_t mask;
+                if (pair_equal(cur, sub_start[q])) { mask = sub_mask[q]; cur = sub_end[q]; }
+                else {
+                    mask = 0;
+                    for (long long n = seg0 + 1; n <= seg1; ++n) {
+                        int j = (int)(n - ts_n0 - 1);
+                        if (pair_step(cur, ts1[j], ts2[j], (uint32_t)(n - w2), p)) mask |= 1u << (int)(n - seg0 - 1);
+                    }
+                    pair_normalise(cur, seg1, w2);
+                }
+                while (mask) {
+                    int bit = __ffs(mask) - 1; mask &= mask - 1;
+                    long long n = seg0 + 1 + bit;
+                    uint32_t en = (uint32_t)(n - w2) - (uint32_t)w1 + 1u;       // event_detector.py:102-104
+                    long long len = (long long)en - (long long)ev_st;
+                    if (len < 1) continue;                                      // :194-195
+                    fire_n[nfire++] = (int)(n - a);
+                    ev_st = en; m_st = ring_latest(n, en % (uint32_t)buf, buf);
+                    if (m_st < 0) m_st = -1;
+                }
             }
         }
         s_nfire = nfire;
@@ -310,6 +342,15 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
     }
     __syncthreads();
     if (s_abort) return;
+    if (s_parallel_emit && tid < nsub) {           // accepted speculative fires -> ordered list, in parallel
+        uint32_t mask = sub_mask[tid];
+        int o = sub_pre[tid];
+        while (mask) {
+            int bit = __ffs(mask) - 1; mask &= mask - 1;
+            fire_n[o++] = tid * SUB + 1 + bit;
+        }
+    }
+    __syncthreads();
 
     // ---- phase E: event table rows (event_detector.py:189-210) --------------------------------
     const int nfire = s_nfire;
@@ -319,13 +360,14 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
     for (int k = tid; k < nfire; k += THREADS) {
         long long n = a + fire_n[k];
         uint32_t en = (uint32_t)(n - w2) - (uint32_t)w1 + 1u;
-        long long m_en = ring_latest(n, en % (uint32_t)buf, buf);
+        const bool steady = fast_ok && a >= (long long)buf;     // slot en%buf still holds S[en]: no 64-bit modulo
+        long long m_en = steady ? (long long)en : ring_latest(n, en % (uint32_t)buf, buf);
         uint32_t st; long long m_st;
         if (k == 0) { st = s_evst0; m_st = s_mst0; }
         else {
             long long np = a + fire_n[k - 1];
             st = (uint32_t)(np - w2) - (uint32_t)w1 + 1u;
-            m_st = ring_latest(np, st % (uint32_t)buf, buf);
+            m_st = steady ? (long long)st : ring_latest(np, st % (uint32_t)buf, buf);
         }
         long long len = (long long)en - (long long)st;
         long long s, q;
