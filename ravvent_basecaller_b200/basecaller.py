@@ -63,7 +63,7 @@ class Basecaller:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and _lib is not None and getattr(_lib, "lib", None) is not None:      # module may be gone at interpreter exit
             _lib.lib.rvb_model_destroy(h)
             self._h = None
 

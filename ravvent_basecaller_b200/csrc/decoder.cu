@@ -53,34 +53,35 @@ __device__ __forceinline__ void warp_topk(float c0, float c1, int n_cand, int W,
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
+template <int WT, int RM, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     extern __shared__ __align__(16) float smem[];
     float *buf = smem;                       // [640][32]: 0..127 prev attention | 128..255 h | 256..511 context
-    float *cs = buf + 640 * RMAX;            // [128][32]
-    float *attn = cs + UNITS * RMAX;         // [128][32]
-    float *qs = attn + UNITS * RMAX;         // [256][32] folded query q' = W_mem . h
-    float *wfc_s = qs + ENC_OUT * RMAX;      // [128*7]
+    float *cs = buf + 640 * RM;            // [128][32]
+    float *attn = cs + UNITS * RM;         // [128][32]
+    float *qs = attn + UNITS * RM;         // [256][32] folded query q' = W_mem . h
+    float *wfc_s = qs + ENC_OUT * RM;      // [128*7]
     float *logit_s = wfc_s + UNITS * VOCAB;  // [32][8]
-    float *lp_s = logit_s + RMAX * 8;        // [32] beam log-probs
-    float *nsc_s = lp_s + RMAX;              // [32] new scores
-    int *tok_s = reinterpret_cast<int *>(nsc_s + RMAX);   // [32]
-    int *fin_s = tok_s + RMAX;               // [32]
-    int *len_s = fin_s + RMAX;               // [32]
-    int *srow_s = len_s + RMAX;              // [32] source row for the reorder
-    int *nidx_s = srow_s + RMAX;             // [32] flat top-k index
-    int *first_s = nidx_s + RMAX;            // [32] greedy: first END step ; beam: per-snippet all-finished step
+    float *lp_s = logit_s + 32 * 8;        // [32] beam log-probs
+    float *nsc_s = lp_s + 32;              // [32] new scores
+    int *tok_s = reinterpret_cast<int *>(nsc_s + 32);   // [32]
+    int *fin_s = tok_s + 32;               // [32]
+    int *len_s = fin_s + 32;               // [32]
+    int *srow_s = len_s + 32;              // [32] source row for the reorder
+    int *nidx_s = srow_s + 32;             // [32] flat top-k index
+    int *first_s = nidx_s + 32;            // [32] greedy: first END step ; beam: per-snippet all-finished step
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = p.W, S = p.S, Tm = p.Tm;
-    const int SN = RMAX / W;
+    const int SN = RM / W;
     const int s0 = blockIdx.x * SN;
     const int ns = min(SN, p.B - s0);
     const int R = ns * W;
 
-    for (int i = tid; i < 640 * RMAX; i += THREADS) buf[i] = 0.0f;
-    for (int i = tid; i < UNITS * RMAX; i += THREADS) { cs[i] = 0.0f; attn[i] = 0.0f; }
+    for (int i = tid; i < 640 * RM; i += THREADS) buf[i] = 0.0f;
+    for (int i = tid; i < UNITS * RM; i += THREADS) { cs[i] = 0.0f; attn[i] = 0.0f; }
     for (int i = tid; i < UNITS * VOCAB; i += THREADS) wfc_s[i] = p.wfc[i];
-    if (tid < RMAX) {
+    if (tid < 32) {
         tok_s[tid] = TOKEN_START;
         int k = tid % W;
         lp_s[tid] = (k == 0) ? 0.0f : -INFINITY;
@@ -95,18 +96,19 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
     for (int t = 0; t < S; ++t) {
         // ---------------- phase 1: LSTM cell on [one_hot(token) | prev attention] ----------------
         {
-            float acc[16][4];
+            constexpr int RH = RM / 2;
+            float acc[RH][4];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                float4 w = __ldg(reinterpret_cast<const float4 *>(p.wtok + ((size_t)tok_s[half * 16 + r] * UNITS + u) * 4));
+            for (int r = 0; r < RH; ++r) {
+                float4 w = __ldg(reinterpret_cast<const float4 *>(p.wtok + ((size_t)tok_s[half * RH + r] * UNITS + u) * 4));
                 acc[r][0] = w.x; acc[r][1] = w.y; acc[r][2] = w.z; acc[r][3] = w.w;
             }
 #pragma unroll 8
             for (int k = 0; k < 2 * UNITS; ++k) {
                 const float4 w = __ldg(reinterpret_cast<const float4 *>(p.wg + ((size_t)k * UNITS + u) * 4));
-                const float4 *xr = reinterpret_cast<const float4 *>(buf + k * RMAX + half * 16);
+                const float4 *xr = reinterpret_cast<const float4 *>(buf + k * RM + half * RH);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < RH / 4; ++q) {
                     const float4 x = xr[q];
                     const float xv[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
@@ -120,13 +122,13 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
             }
             __syncthreads();                 // every read of the old h rows is done
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                int row = half * 16 + r;
-                float c = cs[u * RMAX + row];
+            for (int r = 0; r < RH; ++r) {
+                int row = half * RH + r;
+                float c = cs[u * RM + row];
                 float ig = fsig(acc[r][0]), fg = fsig(acc[r][1]), gg = ftanh(acc[r][2]), og = fsig(acc[r][3]);
                 c = fg * c + ig * gg;
-                cs[u * RMAX + row] = c;
-                buf[(UNITS + u) * RMAX + row] = og * ftanh(c);
+                cs[u * RM + row] = c;
+                buf[(UNITS + u) * RM + row] = og * ftanh(c);
             }
         }
         __syncthreads();
@@ -134,23 +136,23 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
         // ---------------- phase 2a: q' = W_mem . h  (Luong score = keys.h = values.(W_mem.h)) ---------
         // Folding the memory layer into the query means only `values` is streamed per step (A.3).
         {
-            float acc[RMAX];
+            float acc[RM];
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) acc[r] = 0.0f;
+            for (int r = 0; r < RM; ++r) acc[r] = 0.0f;
 #pragma unroll 8
             for (int k = 0; k < UNITS; ++k) {
                 const float w = __ldg(p.wmemT + (size_t)k * ENC_OUT + tid);
-                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RMAX);
+                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RM);
 #pragma unroll
-                for (int q = 0; q < RMAX / 4; ++q) {
+                for (int q = 0; q < RM / 4; ++q) {
                     const float4 x = xr[q];
                     acc[q * 4 + 0] = fmaf(x.x, w, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(x.y, w, acc[q * 4 + 1]);
                     acc[q * 4 + 2] = fmaf(x.z, w, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(x.w, w, acc[q * 4 + 3]);
                 }
             }
 #pragma unroll
-            for (int q = 0; q < RMAX / 4; ++q)
-                *reinterpret_cast<float4 *>(qs + tid * RMAX + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+            for (int q = 0; q < RM / 4; ++q)
+                *reinterpret_cast<float4 *>(qs + tid * RM + q * 4) = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
         }
         __syncthreads();
 
@@ -166,17 +168,17 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
                 const int tt = 8 * lane + j;
                 if (tt < Tm && p.mask[bm + tt] != 0) mbits |= 1u << j;
             }
-            float q[WMAX][8], acc[WMAX][8], mx[WMAX], den[WMAX];
+            float q[WT][8], acc[WT][8], mx[WT], den[WT];
 #pragma unroll
-            for (int w = 0; w < WMAX; ++w) {
+            for (int w = 0; w < WT; ++w) {
                 mx[w] = -INFINITY; den[w] = 0.0f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { acc[w][e] = 0.0f; q[w][e] = 0.0f; }
                 if (w < W) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        q[w][e] = qs[(4 * lane + e) * RMAX + s * W + w];
-                        q[w][4 + e] = qs[(UNITS + 4 * lane + e) * RMAX + s * W + w];
+                        q[w][e] = qs[(4 * lane + e) * RM + s * W + w];
+                        q[w][4 + e] = qs[(UNITS + 4 * lane + e) * RM + s * W + w];
                     }
                 }
             }
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
                 }
                 if (vb_cur != 0) {
 #pragma unroll
-                    for (int w = 0; w < WMAX; ++w)
+                    for (int w = 0; w < WT; ++w)
                         if (w < W) {
                             float sj[4];
 #pragma unroll
@@ -241,14 +243,14 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
                 vb_cur = vb_nxt;
             }
 #pragma unroll
-            for (int w = 0; w < WMAX; ++w)
+            for (int w = 0; w < WT; ++w)
                 if (w < W) {
                     // every position masked: tfa's softmax over all -inf yields NaN; keep that contract
                     const float inv = (den[w] > 0.0f) ? 1.0f / den[w] : __int_as_float(0x7fc00000);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        buf[(2 * UNITS + 4 * lane + e) * RMAX + s * W + w] = acc[w][e] * inv;
-                        buf[(3 * UNITS + 4 * lane + e) * RMAX + s * W + w] = acc[w][4 + e] * inv;
+                        buf[(2 * UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][e] * inv;
+                        buf[(3 * UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][4 + e] * inv;
                     }
                 }
         }
@@ -256,22 +258,23 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
 
         // ---------------- phase 3: attention = [h | context] . W_att ----------------------------------
         {
-            float acc[16];
+            constexpr int RH = RM / 2;
+            float acc[RH];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) acc[r] = 0.0f;
+            for (int r = 0; r < RH; ++r) acc[r] = 0.0f;
 #pragma unroll 8
             for (int k = 0; k < 3 * UNITS; ++k) {
                 const float w = __ldg(p.watt + (size_t)k * UNITS + u);
-                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RMAX + half * 16);
+                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RM + half * RH);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < RH / 4; ++q) {
                     const float4 x = xr[q];
                     acc[q * 4 + 0] = fmaf(x.x, w, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(x.y, w, acc[q * 4 + 1]);
                     acc[q * 4 + 2] = fmaf(x.z, w, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(x.w, w, acc[q * 4 + 3]);
                 }
             }
 #pragma unroll
-            for (int r = 0; r < 16; ++r) attn[u * RMAX + half * 16 + r] = acc[r];
+            for (int r = 0; r < RH; ++r) attn[u * RM + half * RH + r] = acc[r];
         }
         __syncthreads();
 
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
             const int r = tid / VOCAB, v = tid % VOCAB;
             float a = p.bfc[v];
 #pragma unroll 8
-            for (int k = 0; k < UNITS; ++k) a = fmaf(attn[k * RMAX + r], wfc_s[k * VOCAB + v], a);
+            for (int k = 0; k < UNITS; ++k) a = fmaf(attn[k * RM + r], wfc_s[k * VOCAB + v], a);
             logit_s[r * 8 + v] = a;
         }
         __syncthreads();
@@ -354,22 +357,23 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
 
         // ---------------- state hand-over to the next step (beam: gather by parent) ---------------------
         if (!p.beam) {
-            for (int i = tid; i < UNITS * RMAX; i += THREADS) buf[i] = attn[i];
+            for (int i = tid; i < UNITS * RM; i += THREADS) buf[i] = attn[i];
         } else {
-            float hv[16], cv[16];
+            constexpr int NE = UNITS * RM / THREADS;
+            float hv[NE], cv[NE];
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int i = tid + e * THREADS, d = i >> 5, r = i & 31, sr = srow_s[r];
-                hv[e] = buf[(UNITS + d) * RMAX + sr];
-                cv[e] = cs[d * RMAX + sr];
-                buf[d * RMAX + r] = attn[d * RMAX + sr];
+            for (int e = 0; e < NE; ++e) {
+                const int i = tid + e * THREADS, d = i / RM, r = i % RM, sr = srow_s[r];
+                hv[e] = buf[(UNITS + d) * RM + sr];
+                cv[e] = cs[d * RM + sr];
+                buf[d * RM + r] = attn[d * RM + sr];
             }
             __syncthreads();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int i = tid + e * THREADS, d = i >> 5, r = i & 31;
-                buf[(UNITS + d) * RMAX + r] = hv[e];
-                cs[d * RMAX + r] = cv[e];
+            for (int e = 0; e < NE; ++e) {
+                const int i = tid + e * THREADS, d = i / RM, r = i % RM;
+                buf[(UNITS + d) * RM + r] = hv[e];
+                cs[d * RM + r] = cv[e];
             }
         }
         __syncthreads();
@@ -407,21 +411,31 @@ __global__ void __launch_bounds__(THREADS, 1) decoder_kernel(Params p) {
     }
 }
 
-constexpr size_t SMEM_FLOATS = 640 * RMAX + 2 * UNITS * RMAX + ENC_OUT * RMAX + UNITS * VOCAB + RMAX * 8 + 2 * RMAX + 6 * RMAX;
+template <int RM>
+constexpr size_t smem_floats() { return (size_t)640 * RM + 2 * UNITS * RM + ENC_OUT * RM + UNITS * VOCAB + 32 * 8 + 2 * 32 + 6 * 32; }
+
+template <int WT, int RM, int MINB>
+static int launch(const Params &p, cudaStream_t stream) {
+    const size_t smem = smem_floats<RM>() * sizeof(float);
+    RVB_CUDA(cudaFuncSetAttribute(decoder_kernel<WT, RM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int SN = RM / p.W;
+    dim3 grid((unsigned)((p.B + SN - 1) / SN));
+    { ProfScope ps(KK_DECODER, stream);
+      decoder_kernel<WT, RM, MINB><<<grid, THREADS, smem, stream>>>(p); }
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
 
 int run(const Params &p, cudaStream_t stream) {
     if (p.B <= 0 || p.S <= 0) return RVB_OK;
     if (p.Tm > TMAX) return fail(RVB_ERR_ARG, "decoder: memory length %d > %d", p.Tm, TMAX);
     if (p.W < 1 || p.W > WMAX) return fail(RVB_ERR_ARG, "decoder: beam width must be in [1,%d]", WMAX);
-    const size_t smem = SMEM_FLOATS * sizeof(float);
-    RVB_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int SN = RMAX / p.W;
-    dim3 grid((unsigned)((p.B + SN - 1) / SN));
-    { ProfScope ps(KK_DECODER, stream);
-      decoder_kernel<<<grid, THREADS, smem, stream>>>(p); }
-    RVB_LAUNCH_CHECK();
-    count_launch();
-    return RVB_OK;
+    // beam 1 / greedy: 16 rows per CTA and two CTAs per SM, so that one CTA's dense phases overlap the
+    // other's HBM streaming; wider beams: 32 rows (all beams of a snippet stay in one CTA)
+    if (p.W == 1) return launch<1, 16, 2>(p, stream);
+    if (p.W <= 5) return launch<5, 32, 1>(p, stream);
+    return launch<9, 32, 1>(p, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ namespace rvb {
 namespace ed {
 
 constexpr int CH = 2048;
-constexpr int SUB = 32;
+constexpr int SUB = 16;
 constexpr int NSUB = CH / SUB;
 constexpr int HMAX = 256;
 constexpr int WMAX = 32;
@@ -435,7 +435,7 @@ extern "C" int rvb_event_detect(const void *d_signal, int sample_bytes, const in
     if (w1 < 1 || w2 < 1 || w1 > ed::WMAX || w2 > ed::WMAX)
         return fail(RVB_ERR_ARG, "window lengths must be in [1,%d]", ed::WMAX);
     if (n_reads < 0 || !h_read_offsets || !h_event_offsets) return fail(RVB_ERR_ARG, "bad read/event offsets");
-    if (warmup < 0) warmup = 64;
+    if (warmup < 0) warmup = 48;
     if (warmup > ed::HMAX) return fail(RVB_ERR_ARG, "warmup must be <= %d", ed::HMAX);
     if (n_reads == 0) return RVB_OK;
     for (int r = 0; r < n_reads; ++r)

@@ -129,8 +129,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     unsigned char *b_tiles = smem + A_BYTES;                         // [(j*2 + part)*2 + kb]
     float *w0s = reinterpret_cast<float *>(smem + A_BYTES + B_BYTES);   // [(F + 1)][512] layer-0 input rows + bias
     uint64_t *h_ready = reinterpret_cast<uint64_t *>(smem + A_BYTES + B_BYTES + W0_FLOATS * 4);
-    uint64_t *acc_full = h_ready + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 2);
+    uint64_t *acc_full = h_ready + 1;                 // [2]: one per 256-column half
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 3);
 
     uint32_t rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -150,7 +150,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     }
     if (threadIdx.x == 0) {
         mbar_init(h_ready, 16);          // 8 epilogue warps x 2 CTAs (only the leader CTA's copy is used)
-        mbar_init(acc_full, 1);
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -190,7 +191,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                             }
                     }
                 }
-                umma_commit_2sm(acc_full);
+                // one commit for both halves: the epilogue rewrites the h tiles (A operand), which every MMA of
+                // the step reads, so it may only start when all of them have retired
+                umma_commit_2sm(&acc_full[0]);
             }
         }
     } else if (warp >= 2) {
@@ -227,6 +230,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
         if (lane == 0) mbar_arrive_remote(h_ready, 0);
 
         bool ok = true;
+        float4 gnext[4];                       // pre-gates of the NEXT 16-column sub-chunk (software pipeline)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gnext[i] = make_float4(0, 0, 0, 0);
         float *so = (p.state_out != nullptr && live) ? p.state_out + (((size_t)b * 2 + dir) * 2) * UNITS + 64 * hlf : nullptr;
         for (int s = 0; s < T && ok; ++s) {
             const int t = dir ? T - 1 - s : s;
@@ -236,8 +242,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 for (int f = 0; f < F; ++f) xin[f] = live ? __ldg(p.x + ((size_t)b * T + t) * F + f) : 0.0f;
             }
             const float *grow = PRE ? p.G + (size_t)b * p.g_bs + (size_t)t * p.g_ts + dir * GATES + 256 * hlf : nullptr;
+            const float *grow_next = nullptr;
+            if (PRE && s + 1 < T) {
+                const int tn = dir ? T - 2 - s : s + 1;
+                grow_next = p.G + (size_t)b * p.g_bs + (size_t)tn * p.g_ts + dir * GATES + 256 * hlf;
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(grow_next + 32 * i));
+                }
+            }
+            if (PRE && s == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
+            }
             float *yrow = p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf;
-            ok = mbar_wait_cluster(acc_full, s & 1, p.abort_flag);
+            ok = mbar_wait_cluster(&acc_full[0], s & 1, p.abort_flag);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -251,9 +270,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                     float z[16];
                     if (PRE) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 g = live ? __ldg(reinterpret_cast<const float4 *>(grow + col + i)) : make_float4(0, 0, 0, 0);
-                            z[i] = g.x; z[i + 1] = g.y; z[i + 2] = g.z; z[i + 3] = g.w;
+                        for (int i = 0; i < 4; ++i) { z[4 * i] = gnext[i].x; z[4 * i + 1] = gnext[i].y; z[4 * i + 2] = gnext[i].z; z[4 * i + 3] = gnext[i].w; }
+                        // issue the loads of the following sub-chunk (or of the next step's first one) now
+                        const float *nsrc = (col + 16 < 256) ? grow + col + 16 : grow_next;
+                        if (live && nsrc != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) gnext[i] = __ldg(reinterpret_cast<const float4 *>(nsrc + 4 * i));
                         }
                     } else {
                         const float *wr = w0s + 256 * hlf + col;
