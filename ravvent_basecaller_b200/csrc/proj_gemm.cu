@@ -118,6 +118,9 @@ int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bi
     if (M <= 0) return RVB_OK;
     if (N % 128 != 0 || K % tc::BK != 0) return fail(RVB_ERR_ARG, "gemm_tc: N %% 128 and K %% 32 must be 0 (N=%d K=%d)", N, K);
     const bool three = (precision == RVB_PREC_FP32);
+    static const bool legacy = getenv("RVB_GEMM_NONPERSISTENT") != nullptr;      // A/B switch for profiling
+    if (N % 256 == 0 && !legacy) return three ? tc::launch_persistent<3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
+                                              : tc::launch_persistent<1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
     if (N % 256 == 0) return three ? tc::launch<256, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
                                    : tc::launch<256, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
     return three ? tc::launch<128, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)

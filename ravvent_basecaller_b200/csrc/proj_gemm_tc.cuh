@@ -245,6 +245,190 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Persistent variant (BN = 256): one CTA per SM loops over output tiles.  Two TMEM accumulator stages
+// (2 x 256 columns) let the epilogue of tile i overlap the mainloop of tile i+1; the A split and the
+// epilogue run on separate warp groups; C leaves through a 128-byte-swizzled staging buffer and TMA
+// stores (cp.async.bulk.tensor ... global.shared::cta), which are fully coalesced and clip the ragged
+// last row tile in hardware.
+//   w0 TMA producer | w1 MMA issuer + TMEM alloc | w4..w7 A split (NPASS == 3) | w8..w11 epilogue
+// ---------------------------------------------------------------------------------------------------
+constexpr int PTHREADS = 384;
+constexpr int PBN = 256;
+constexpr int CSTAGE_BYTES = BM * 32 * 4;       // 128 rows x 32 fp32 columns
+
+template <int NPASS>
+struct PCfg {
+    static constexpr int A_BYTES = BM * BK * 4;
+    static constexpr int B_BYTES = PBN * BK * 4;
+    static constexpr int STAGE_BYTES = (NPASS == 3) ? (2 * A_BYTES + 2 * B_BYTES) : (A_BYTES + B_BYTES);
+    static constexpr int STAGES = (NPASS == 3) ? 2 : 4;
+    static constexpr int TX_BYTES = A_BYTES + ((NPASS == 3) ? 2 : 1) * B_BYTES;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(PTHREADS, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                          const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
+                          const float *__restrict__ bias, long long M, int N, int K, int *abort_flag) {
+    using cfg = PCfg<NPASS>;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char *cstage = smem + (size_t)cfg::STAGES * cfg::STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + 2 * CSTAGE_BYTES);
+    uint64_t *full = bars, *ready = bars + cfg::STAGES, *empty = bars + 2 * cfg::STAGES;
+    uint64_t *acc_full = bars + 3 * cfg::STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = N / PBN;
+    const long long total = (long long)n_tiles * ((M + BM - 1) / BM);
+    const int num_kb = K / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    auto stage_a = [&](int s) { return smem + (size_t)s * cfg::STAGE_BYTES; };
+    auto stage_bhi = [&](int s) { return stage_a(s) + ((NPASS == 3) ? 2 : 1) * cfg::A_BYTES; };
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer =====
+            long long g = 0; bool ok = true;
+            for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+                const int n_tile = (int)(tile % n_tiles); const long long m_tile = tile / n_tiles;
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
+                    if (round > 0 && !mbar_wait(&empty[s], (uint32_t)((round - 1) & 1), abort_flag)) { ok = false; break; }
+                    mbar_expect_tx(&full[s], cfg::TX_BYTES);
+                    tma_load_2d(&map_a, &full[s], stage_a(s), kb * BK, (int)(m_tile * BM));
+                    tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kb * BK, n_tile * PBN);
+                    if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kb * BK, n_tile * PBN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ===== MMA issuer =====
+            constexpr uint32_t idesc = make_idesc_tf32(BM, PBN);
+            long long g = 0, it = 0; bool ok = true;
+            for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++it) {
+                const int as = (int)(it & 1); const long long ar = it >> 1;
+                if (ar > 0 && !mbar_wait(&acc_empty[as], (uint32_t)((ar - 1) & 1), abort_flag)) { ok = false; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem_base + (uint32_t)(as * PBN);
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
+                    if (!mbar_wait((NPASS == 3) ? &ready[s] : &full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_bhi(s));
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+                        const uint32_t koff = ks * UMMA_K * 4;
+                        const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+                        if (NPASS == 3) {
+                            umma_tf32(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
+                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
+                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+                        } else {
+                            umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                if (ok) umma_commit(&acc_full[as]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        if (NPASS == 3) {                                  // ===== A split: hi in place, lo to the sibling buffer =====
+            const int et = threadIdx.x - 128;
+            long long g = 0; bool ok = true;
+            for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
+                    if (!mbar_wait(&full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
+                    float4 *hi = reinterpret_cast<float4 *>(stage_a(s));
+                    float4 *lo = reinterpret_cast<float4 *>(stage_a(s) + cfg::A_BYTES);
+#pragma unroll
+                    for (int i = 0; i < cfg::A_BYTES / 16 / 128; ++i) {
+                        float4 v = hi[et + i * 128];
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                        hi[et + i * 128] = h;
+                        lo[et + i * 128] = l;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&ready[s]);
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue: TMEM -> registers (+bias) -> swizzled smem staging -> TMA store =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                     // row of the tile == TMEM lane
+        const int et = threadIdx.x - 256;
+        long long it = 0; int chunk_ctr = 0; bool ok = true;
+        for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++it) {
+            const int n_tile = (int)(tile % n_tiles); const long long m_tile = tile / n_tiles;
+            const int as = (int)(it & 1); const long long ar = it >> 1;
+            if (!mbar_wait(&acc_full[as], (uint32_t)(ar & 1), abort_flag)) { ok = false; break; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < PBN; c0 += 32, ++chunk_ctr) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PBN + c0), r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 == PBN) {                      // accumulator stage fully read: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&acc_empty[as]);
+                }
+                unsigned char *cb = cstage + (chunk_ctr & 1) * CSTAGE_BYTES;
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store that last used cb has read it
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    if (bias != nullptr) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)n_tile * PBN + c0 + 4 * j));
+                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                    }
+                    *reinterpret_cast<float4 *>(cb + row * 128 + ((j ^ (row & 7)) << 4)) = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    tma_store_2d(&map_c, cb, n_tile * PBN + c0, (int)(m_tile * BM));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -264,12 +448,12 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major [rows, cols] tensor, box = BK columns x box_rows rows, 128-byte swizzle.
-inline int make_map(CUtensorMap *map, const float *base, long long rows, int cols, int box_rows) {
+inline int make_map(CUtensorMap *map, const float *base, long long rows, int cols, int box_rows, int box_cols = BK) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -292,6 +476,28 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
     dim3 grid((unsigned)tiles);
     { ProfScope ps(KK_GEMM, stream);
       gemm_tc_kernel<BN, NPASS><<<grid, THREADS, cfg::SMEM, stream>>>(ma, mh, ml, bias, C, M, N, K, abort_flag); }
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+
+template <int NPASS>
+int launch_persistent(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N,
+                      int K, int *abort_flag, cudaStream_t stream) {
+    using cfg = PCfg<NPASS>;
+    CUtensorMap ma, mh, ml, mc;
+    RVB_CHECK(make_map(&ma, A, M, K, BM));
+    RVB_CHECK(make_map(&mh, WhiT, N, K, PBN));
+    RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, PBN));
+    RVB_CHECK(make_map(&mc, C, M, N, BM, 32));
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (long long)(N / PBN) * ((M + BM - 1) / BM);
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    { ProfScope ps(KK_GEMM, stream);
+      gemm_tc_persistent_kernel<NPASS><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mh, ml, mc, bias, M, N, K, abort_flag); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;
