@@ -43,7 +43,7 @@ REC_FLOP_PER_STEP_ROW = 131072            # recurrent FLOPs per timestep per dir
 REC_BYTES_L0 = 512 + 4                    # per step per row per direction, raw layer 0 (write h + read x)
 REC_BYTES_L1 = 2560                       # layer > 0: read 512 pre-gates + write 128 h (fp32)
 # dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/), 9472-chunk wave
-NCU_TRAFFIC = {"recurrent_lstm": 9.72e9, "decoder": None, "projection_gemm": None}
+NCU_TRAFFIC = {"recurrent_lstm": 9.71e9, "decoder": 63.7e9, "projection_gemm": 9.65e9}
 
 
 def synth_chunks(rng, n):
@@ -290,9 +290,9 @@ def run_ours(args, rank, local_rank, world):
                          "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms1 * args.steps),
                          "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
                          "achieved_tflops": kr[dom]["tflops"],
-                         "note": "fp32-parity mode keeps the LSTM recurrence on the FFMA pipe (56%% of the 74.5 TFLOP/s "
-                                 "FP32 peak), so this kernel is FP32-issue bound, not HBM bound; achieved = algorithmic "
-                                 "bytes (DESIGN.md §5) / CUDA-event time"},
+                         "note": "achieved = algorithmic bytes (DESIGN.md 4-5) / CUDA-event time of the kernel's launches in the "
+                                 "timed region; traffic = dram bytes of ONE launch on a 9472-chunk wave from the committed ncu "
+                                 "capture (profiles/), scale by chunks/9472 to compare with a full step"},
             "kernels": kr,
             "event_path": event_path_bench(local_rank) if not args.no_event_path else None,
         }

@@ -246,10 +246,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
             if (PRE && s + 1 < T) {
                 const int tn = dir ? T - 2 - s : s + 1;
                 grow_next = p.G + (size_t)b * p.g_bs + (size_t)tn * p.g_ts + dir * GATES + 256 * hlf;
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(grow_next + 32 * i));
-                }
             }
             if (PRE && s == 0) {
 #pragma unroll
