@@ -60,6 +60,8 @@ struct rvb_model {
     float *d_pb[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_phi[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // tf32 hi part, [N,K]
     float *d_plo[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // remainder, [N,K]
+    void *d_phi16[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // fp16 hi part, [N,K]
+    void *d_plo16[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     int *d_abort = nullptr;
     bool rec_tc = false;                       // recurrences on tcgen05 (lstm_recurrent_tc.cu)
     uint16_t *d_bimg[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
@@ -243,6 +245,13 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
                 RVB_CHECK(dmalloc(m, &m->d_phi[e][l], wcat.size()));
                 RVB_CHECK(dmalloc(m, &m->d_plo[e][l], wcat.size()));
                 RVB_CHECK(gemm::prepare_weights(m->d_pw[e][l], m->d_phi[e][l], m->d_plo[e][l], ENC_OUT, 2 * GATES, nullptr));
+                if (m->rec_tc) {
+                    uint16_t *h16 = nullptr, *l16 = nullptr;
+                    RVB_CHECK(dmalloc(m, &h16, wcat.size()));
+                    RVB_CHECK(dmalloc(m, &l16, wcat.size()));
+                    m->d_phi16[e][l] = h16; m->d_plo16[e][l] = l16;
+                    RVB_CHECK(gemm::prepare_weights_f16(m->d_pw[e][l], h16, l16, ENC_OUT, 2 * GATES, nullptr));
+                }
             }
         }
     }
@@ -337,11 +346,19 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
         p.bimg = m->d_bimg[e][l]; p.w0 = m->d_w0[e];
         p.state_in = l == 0 ? nullptr : m->st[e][(l - 1) & 1];
         p.state_out = m->st[e][l & 1];
-        p.y = last ? out + (size_t)t_off * ENC_OUT : yb[l & 1];
-        p.y_bs = last ? (long long)Tm * ENC_OUT : ENC_OUT;
-        p.y_ts = last ? ENC_OUT : (long long)nb * ENC_OUT;
+        // intermediate layers hand their output to K2 as fp16 hi/lo planes (time-major, same bytes as fp32)
+        uint16_t *pl_hi = reinterpret_cast<uint16_t *>(yb[l & 1]);
+        uint16_t *pl_lo = pl_hi + (size_t)nb * T * ENC_OUT;
+        p.y = last ? out + (size_t)t_off * ENC_OUT : nullptr;
+        p.y_bs = (long long)Tm * ENC_OUT; p.y_ts = ENC_OUT;
+        p.y16_hi = last ? nullptr : pl_hi; p.y16_lo = last ? nullptr : pl_lo;
+        p.y16_bs = ENC_OUT; p.y16_ts = (long long)nb * ENC_OUT;
         p.B = nb; p.T = T; p.abort_flag = m->d_abort;
-        if (l > 0) RVB_CHECK(project(m, e, l, yb[(l - 1) & 1], G, (long long)nb * T, s));
+        if (l > 0) {
+            const uint16_t *a_hi = reinterpret_cast<const uint16_t *>(yb[(l - 1) & 1]);
+            RVB_CHECK(gemm::run_tc_f16(a_hi, a_hi + (size_t)nb * T * ENC_OUT, m->d_phi16[e][l], m->d_plo16[e][l], m->d_pb[e][l], G,
+                                       (long long)nb * T, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s));
+        }
         RVB_CHECK(rectc::run(l == 0 ? feat : 0, p, s));
     }
     for (int l = 0; l < m->enc_depth && !m->rec_tc; ++l) {
@@ -556,6 +573,26 @@ extern "C" int rvb_project(const float *d_a, const float *d_b, const float *d_bi
     if (!d_a || !d_b || !d_c || mrows < 0 || n <= 0 || k <= 0) return fail(RVB_ERR_ARG, "project: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     if (precision == -1) return gemm::run_simt(d_a, d_b, d_bias, d_c, mrows, n, k, s);
+    if (precision == 2 || precision == 3) {
+        // fp16-plane variant (what the encoders use between layers): split A and W into fp16 hi/lo planes first
+        char *scratch16 = nullptr;
+        const size_t na = (size_t)mrows * k, nw = (size_t)n * k;
+        RVB_CUDA(cudaMalloc(&scratch16, (2 * na + 2 * nw) * 2 + 64));
+        uint16_t *ahi = reinterpret_cast<uint16_t *>(scratch16), *alo = ahi + na, *whi = alo + na, *wlo = whi + nw;
+        int *flag16 = reinterpret_cast<int *>(wlo + nw + (nw & 1));
+        int st16 = RVB_OK;
+        if (cudaMemsetAsync(flag16, 0, sizeof(int), s) != cudaSuccess) st16 = fail(RVB_ERR_CUDA, "memset");
+        if (st16 == RVB_OK) st16 = gemm::split_planes_f16(d_a, ahi, alo, (long long)na, s);
+        if (st16 == RVB_OK) st16 = gemm::prepare_weights_f16(d_b, whi, wlo, k, n, s);
+        if (st16 == RVB_OK) st16 = gemm::run_tc_f16(ahi, alo, whi, wlo, d_bias, d_c, mrows, n, k, precision == 2 ? RVB_PREC_FP32 : RVB_PREC_BF16, flag16, s);
+        int hf = 0;
+        cudaError_t e16 = cudaStreamSynchronize(s);
+        if (st16 == RVB_OK && e16 != cudaSuccess) st16 = fail(RVB_ERR_CUDA, "project: %s", cudaGetErrorString(e16));
+        if (st16 == RVB_OK) cudaMemcpy(&hf, flag16, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(scratch16);
+        if (st16 == RVB_OK && hf != 0) st16 = fail(RVB_ERR_INTERNAL, "project: tcgen05 kernel timed out on an mbarrier");
+        return st16;
+    }
     if (precision != RVB_PREC_FP32 && precision != RVB_PREC_BF16) return fail(RVB_ERR_ARG, "project: bad precision");
     // standalone entry (tests / roofline): split + transpose the weights into scratch, run, check the abort flag
     float *scratch = nullptr;

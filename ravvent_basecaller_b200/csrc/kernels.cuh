@@ -28,8 +28,10 @@ struct Params {
     const float *w0;            // [dir][6][512] layer-0 input rows + bias row, [unit][gate] column order
     const float *state_in;      // [B,2,2,128] or nullptr
     float *state_out;
-    float *y;                   // (b,t,dir*128+u) at y[b*y_bs + t*y_ts + dir*128 + u]
+    float *y;                   // (b,t,dir*128+u) at y[b*y_bs + t*y_ts + dir*128 + u]   (nullptr when planes are written)
     long long y_bs, y_ts;
+    uint16_t *y16_hi, *y16_lo;  // optional fp16 hi / lo planes of the same logical tensor (input of the next K2)
+    long long y16_bs, y16_ts;
     int B, T;
     int *abort_flag;
 };
@@ -46,6 +48,11 @@ int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaSt
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
            int precision, int *abort_flag, cudaStream_t s);
 bool tc_available();
+// fp16-plane path (A produced as hi/lo planes by K3): all operands fp16, 3 passes on the fp16 pipe
+int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t s);
+int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cudaStream_t s);
+int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
+               int N, int K, int precision, int *abort_flag, cudaStream_t s);
 }  // namespace gemm
 
 namespace dec {     // K4 + K5, decoder.cu

@@ -35,6 +35,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ftanh(float x) { return 2.0f * fsig(2.0f * x) - 1.0f; }
 
+// LSTM cell pointwise math with shared reciprocals: 5 ex2 + 3 rcp per unit instead of 5 + 5.
+//   i*g      = (1/A)(1 - 2/G) = (G - 2) / (A*G)          A = 1 + e^-zi,  G = 1 + e^{2 zg}
+//   f, o     : r = 1/(F*O);  f = r*O,  o = r*F            F = 1 + e^-zf,  O = 1 + e^-zo
+//   o*tanh(c'): o * (Cc - 2) / Cc                         Cc = 1 + e^{2 c'}
+// Arguments are clamped where the functions are saturated to < 1e-13 of their limit, which keeps every
+// product below 1e27 (no fp32 overflow).
+__device__ __forceinline__ void lstm_pointwise(float zi, float zf, float zg, float zo, float c, float &cn, float &hn) {
+    const float A = 1.0f + __expf(-fminf(fmaxf(zi, -30.0f), 30.0f));
+    const float F = 1.0f + __expf(-fminf(fmaxf(zf, -30.0f), 30.0f));
+    const float O = 1.0f + __expf(-fminf(fmaxf(zo, -30.0f), 30.0f));
+    const float G = 1.0f + __expf(2.0f * fminf(fmaxf(zg, -15.0f), 15.0f));
+    const float ig = (G - 2.0f) * __fdividef(1.0f, A * G);
+    const float r = __fdividef(1.0f, F * O);
+    cn = c * (r * O) + ig;
+    const float Cc = 1.0f + __expf(2.0f * fminf(fmaxf(cn, -15.0f), 15.0f));
+    hn = (r * F) * (Cc - 2.0f) * __fdividef(1.0f, Cc);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -107,7 +125,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // Store 8 consecutive units of h (k = 64*kb + 8*chunk .. +7) of `row` as fp16 hi and lo into the A tiles.
-__device__ __forceinline__ void store_h8(unsigned char *a_tiles, int row, int kb, int chunk, const float (&h)[8]) {
+__device__ __forceinline__ void store_h8(unsigned char *a_tiles, int row, int kb, int chunk, const float (&h)[8],
+                                         uint4 &hi_out, uint4 &lo_out) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -117,8 +136,10 @@ __device__ __forceinline__ void store_h8(unsigned char *a_tiles, int row, int kb
         lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
     const int off = kb * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
-    *reinterpret_cast<uint4 *>(a_tiles + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4 *>(a_tiles + 2 * TILE_BYTES + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    hi_out = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    lo_out = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4 *>(a_tiles + off) = hi_out;
+    *reinterpret_cast<uint4 *>(a_tiles + 2 * TILE_BYTES + off) = lo_out;
 }
 
 template <int F, bool PRE>
@@ -222,7 +243,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 float h8[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) h8[u] = h0[8 * ch + u];
-                store_h8(a_tiles, row, hlf, ch, h8);
+                uint4 dh, dl;
+                store_h8(a_tiles, row, hlf, ch, h8, dh, dl);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -251,7 +273,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
             }
-            float *yrow = p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf;
+            float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf : nullptr;
             ok = mbar_wait_cluster(&acc_full[0], s & 1, p.abort_flag);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -295,15 +317,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                         const float zg = z[4 * u + 2] + __uint_as_float(r[4 * u + 2]);
                         const float zo = z[4 * u + 3] + __uint_as_float(r[4 * u + 3]);
                         const int ci = 8 * ch + 4 * sub + u;
-                        const float cn = fsig(zf) * c[ci] + fsig(zi) * ftanh(zg);
+                        float cn, hn;
+                        lstm_pointwise(zi, zf, zg, zo, c[ci], cn, hn);
                         c[ci] = cn;
-                        h8[4 * sub + u] = fsig(zo) * ftanh(cn);
+                        h8[4 * sub + u] = hn;
                     }
                 }
-                store_h8(a_tiles, row, hlf, ch, h8);
+                uint4 ph, pl;
+                store_h8(a_tiles, row, hlf, ch, h8, ph, pl);
                 if (live) {
-                    *reinterpret_cast<float4 *>(yrow + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
-                    *reinterpret_cast<float4 *>(yrow + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);
+                    if (p.y16_hi != nullptr) {          // intermediate layer: fp16 hi/lo planes for the next projection
+                        const size_t o = (size_t)b * p.y16_bs + (size_t)t * p.y16_ts + dir * UNITS + 64 * hlf + 8 * ch;
+                        *reinterpret_cast<uint4 *>(p.y16_hi + o) = ph;
+                        *reinterpret_cast<uint4 *>(p.y16_lo + o) = pl;
+                    } else {
+                        *reinterpret_cast<float4 *>(yrow + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
+                        *reinterpret_cast<float4 *>(yrow + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);
+                    }
                     if (so != nullptr && s == T - 1) {
                         *reinterpret_cast<float4 *>(so + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
                         *reinterpret_cast<float4 *>(so + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);

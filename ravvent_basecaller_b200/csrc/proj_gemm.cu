@@ -11,6 +11,7 @@
 //     when debugging; the model path never selects it implicitly.
 #include "kernels.cuh"
 #define RVB_HAVE_TC 1
+#include <cuda_fp16.h>
 #include "proj_gemm_tc.cuh"
 
 namespace rvb {
@@ -119,12 +120,53 @@ int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bi
     if (N % 128 != 0 || K % tc::BK != 0) return fail(RVB_ERR_ARG, "gemm_tc: N %% 128 and K %% 32 must be 0 (N=%d K=%d)", N, K);
     const bool three = (precision == RVB_PREC_FP32);
     static const bool legacy = getenv("RVB_GEMM_NONPERSISTENT") != nullptr;      // A/B switch for profiling
-    if (N % 256 == 0 && !legacy) return three ? tc::launch_persistent<3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
-                                              : tc::launch_persistent<1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+    if (N % 256 == 0 && !legacy) return three ? tc::launch_persistent<3, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
+                                              : tc::launch_persistent<1, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
     if (N % 256 == 0) return three ? tc::launch<256, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
                                    : tc::launch<256, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
     return three ? tc::launch<128, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
                  : tc::launch<128, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+}
+
+// ---- fp16-plane path: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) ------------------------------------
+__global__ void split_f16_kernel(const float *__restrict__ X, __half *__restrict__ hi, __half *__restrict__ lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = X[i];
+    const __half h = __float2half_rn(v);
+    hi[i] = h;
+    lo[i] = __float2half_rn(v - __half2float(h));
+}
+// W[K,N] fp32 row-major -> fp16 hi / lo planes transposed to [N,K]
+__global__ void split_transpose_f16_kernel(const float *__restrict__ W, __half *__restrict__ hiT, __half *__restrict__ loT, int K, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const int n = i / K, k = i % K;
+    const float v = W[(size_t)k * N + n];
+    const __half h = __float2half_rn(v);
+    hiT[i] = h;
+    loT[i] = __float2half_rn(v - __half2float(h));
+}
+int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t stream) {
+    if (n <= 0) return RVB_OK;
+    split_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(X, reinterpret_cast<__half *>(hi), reinterpret_cast<__half *>(lo), n);
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cudaStream_t stream) {
+    const int n = K * N;
+    split_transpose_f16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W, reinterpret_cast<__half *>(hiT), reinterpret_cast<__half *>(loT), K, N);
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
+               int N, int K, int precision, int *abort_flag, cudaStream_t stream) {
+    if (M <= 0) return RVB_OK;
+    if (N % 256 != 0 || K % 64 != 0) return fail(RVB_ERR_ARG, "gemm_tc_f16: N %% 256 and K %% 64 must be 0 (N=%d K=%d)", N, K);
+    if (precision == RVB_PREC_FP32) return tc::launch_persistent<3, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+    return tc::launch_persistent<1, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
 }
 
 }  // namespace gemm

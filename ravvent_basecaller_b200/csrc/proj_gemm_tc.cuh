@@ -84,6 +84,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate), K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -256,13 +267,15 @@ constexpr int PTHREADS = 384;
 constexpr int PBN = 256;
 constexpr int CSTAGE_BYTES = BM * 32 * 4;       // 128 rows x 32 fp32 columns
 
-template <int NPASS>
+template <int NPASS, bool F16IN = false>
 struct PCfg {
     static constexpr int A_BYTES = BM * BK * 4;
     static constexpr int B_BYTES = PBN * BK * 4;
     static constexpr int STAGE_BYTES = (NPASS == 3) ? (2 * A_BYTES + 2 * B_BYTES) : (A_BYTES + B_BYTES);
     static constexpr int STAGES = (NPASS == 3) ? 2 : 4;
-    static constexpr int TX_BYTES = A_BYTES + ((NPASS == 3) ? 2 : 1) * B_BYTES;
+    // fp16-plane inputs: A_lo also arrives by TMA; a stage then covers 64 K-elements (128 bytes of fp16)
+    static constexpr int TX_BYTES = ((NPASS == 3 && F16IN) ? 2 : 1) * A_BYTES + ((NPASS == 3) ? 2 : 1) * B_BYTES;
+    static constexpr int K_PER_STAGE = F16IN ? 64 : 32;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 1024 + 256;
 };
 
@@ -271,12 +284,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int NPASS>
+template <int NPASS, bool F16IN>
 __global__ void __launch_bounds__(PTHREADS, 1)
-gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                          const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c,
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
+                          const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                          const __grid_constant__ CUtensorMap map_c,
                           const float *__restrict__ bias, long long M, int N, int K, int *abort_flag) {
-    using cfg = PCfg<NPASS>;
+    using cfg = PCfg<NPASS, F16IN>;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char *cstage = smem + (size_t)cfg::STAGES * cfg::STAGE_BYTES;
@@ -288,7 +302,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = N / PBN;
     const long long total = (long long)n_tiles * ((M + BM - 1) / BM);
-    const int num_kb = K / BK;
+    const int num_kb = K / cfg::K_PER_STAGE;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
@@ -316,15 +330,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
                     if (round > 0 && !mbar_wait(&empty[s], (uint32_t)((round - 1) & 1), abort_flag)) { ok = false; break; }
                     mbar_expect_tx(&full[s], cfg::TX_BYTES);
-                    tma_load_2d(&map_a, &full[s], stage_a(s), kb * BK, (int)(m_tile * BM));
-                    tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kb * BK, n_tile * PBN);
-                    if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kb * BK, n_tile * PBN);
+                    const int kc = kb * cfg::K_PER_STAGE;
+                    tma_load_2d(&map_a, &full[s], stage_a(s), kc, (int)(m_tile * BM));
+                    if (NPASS == 3 && F16IN) tma_load_2d(&map_alo, &full[s], stage_a(s) + cfg::A_BYTES, kc, (int)(m_tile * BM));
+                    tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kc, n_tile * PBN);
+                    if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kc, n_tile * PBN);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ===== MMA issuer =====
-            constexpr uint32_t idesc = make_idesc_tf32(BM, PBN);
+            constexpr uint32_t idesc = F16IN ? make_idesc_f16(BM, PBN) : make_idesc_tf32(BM, PBN);
             long long g = 0, it = 0; bool ok = true;
             for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++it) {
                 const int as = (int)(it & 1); const long long ar = it >> 1;
@@ -333,14 +349,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 const uint32_t d = tmem_base + (uint32_t)(as * PBN);
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
-                    if (!mbar_wait((NPASS == 3) ? &ready[s] : &full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
+                    if (!mbar_wait((NPASS == 3 && !F16IN) ? &ready[s] : &full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_bhi(s));
 #pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-                        const uint32_t koff = ks * UMMA_K * 4;
+                    for (int ks = 0; ks < 4; ++ks) {            // 4 x 32 bytes of K per 128-byte swizzle row
+                        const uint32_t koff = ks * 32;
                         const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                        if (NPASS == 3) {
+                        if (F16IN) {
+                            if (NPASS == 3) {
+                                umma_f16(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
+                                umma_f16(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
+                                umma_f16(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+                            } else {
+                                umma_f16(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+                            }
+                        } else if (NPASS == 3) {
                             umma_tf32(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
                             umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
                             umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
@@ -354,7 +378,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             }
         }
     } else if (warp >= 4 && warp < 8) {
-        if (NPASS == 3) {                                  // ===== A split: hi in place, lo to the sibling buffer =====
+        if (NPASS == 3 && !F16IN) {                        // ===== A split: hi in place, lo to the sibling buffer =====
             const int et = threadIdx.x - 128;
             long long g = 0; bool ok = true;
             for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
@@ -448,14 +472,14 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major [rows, cols] tensor, box = BK columns x box_rows rows, 128-byte swizzle.
-inline int make_map(CUtensorMap *map, const float *base, long long rows, int cols, int box_rows, int box_cols = BK) {
+inline int make_map(CUtensorMap *map, const void *base, long long rows, int cols, int box_rows, int box_cols = BK, bool f16 = false) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * (f16 ? 2 : 4)};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+    CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -481,23 +505,26 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
     return RVB_OK;
 }
 
-template <int NPASS>
-int launch_persistent(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N,
-                      int K, int *abort_flag, cudaStream_t stream) {
-    using cfg = PCfg<NPASS>;
-    CUtensorMap ma, mh, ml, mc;
-    RVB_CHECK(make_map(&ma, A, M, K, BM));
-    RVB_CHECK(make_map(&mh, WhiT, N, K, PBN));
-    RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, PBN));
+// F16IN: A (and W) are given as fp16 hi / lo planes ([M,K] / [N,K] row-major), K-elements per stage = 64.
+template <int NPASS, bool F16IN>
+int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
+                      long long M, int N, int K, int *abort_flag, cudaStream_t stream) {
+    using cfg = PCfg<NPASS, F16IN>;
+    CUtensorMap ma, mal, mh, ml, mc;
+    const int bk = cfg::K_PER_STAGE;
+    RVB_CHECK(make_map(&ma, A, M, K, BM, bk, F16IN));
+    RVB_CHECK(make_map(&mal, (NPASS == 3 && F16IN) ? Alo : A, M, K, BM, bk, F16IN));
+    RVB_CHECK(make_map(&mh, WhiT, N, K, PBN, bk, F16IN));
+    RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, PBN, bk, F16IN));
     RVB_CHECK(make_map(&mc, C, M, N, BM, 32));
-    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)(N / PBN) * ((M + BM - 1) / BM);
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     { ProfScope ps(KK_GEMM, stream);
-      gemm_tc_persistent_kernel<NPASS><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mh, ml, mc, bias, M, N, K, abort_flag); }
+      gemm_tc_persistent_kernel<NPASS, F16IN><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc, bias, M, N, K, abort_flag); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;
