@@ -29,7 +29,8 @@ constexpr int TILE_BYTES = 16384;     // [128 rows][64 fp16] K-major SW128 tile
 constexpr int A_BYTES = 4 * TILE_BYTES;     // (hi|lo) x (kb 0|1)
 constexpr int B_BYTES = 8 * TILE_BYTES;     // (half j) x (hi|lo) x (kb)
 constexpr int W0_FLOATS = 6 * GATES;        // layer 0: up to 5 feature rows + bias, [unit][gate] order
-constexpr size_t SMEM = 1024 + A_BYTES + B_BYTES + W0_FLOATS * 4 + 256;
+constexpr int ALT_BYTES = 2 * TILE_BYTES;   // ping-pong copy of the (hi|lo) kb 0 tiles, see the kernel comment
+constexpr size_t SMEM = 1024 + A_BYTES + ALT_BYTES + B_BYTES + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -56,13 +57,15 @@ __device__ __forceinline__ void lstm_pointwise(float zi, float zf, float zg, flo
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, int *abort_flag) {
+// Bounded wait with the default (CTA-scope) acquire.  NOTE: never poll with `.acquire.cluster`: every such
+// try_wait makes ptxas emit CCTL.IVALL (L1 invalidate) -- it was 24 % of this kernel's stall samples.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *abort_flag) {
     const uint32_t addr = smem_u32(bar);
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return true;
@@ -75,7 +78,7 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -125,7 +128,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 // Store 8 consecutive units of h (k = 64*kb + 8*chunk .. +7) of `row` as fp16 hi and lo into the A tiles.
-__device__ __forceinline__ void store_h8(unsigned char *a_tiles, int row, int kb, int chunk, const float (&h)[8],
+__device__ __forceinline__ void store_h8(unsigned char *hi_tile, unsigned char *lo_tile, int row, int chunk, const float (&h)[8],
                                          uint4 &hi_out, uint4 &lo_out) {
     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -135,11 +138,11 @@ __device__ __forceinline__ void store_h8(unsigned char *a_tiles, int row, int kb
         hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
         lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
-    const int off = kb * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
+    const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
     hi_out = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     lo_out = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4 *>(a_tiles + off) = hi_out;
-    *reinterpret_cast<uint4 *>(a_tiles + 2 * TILE_BYTES + off) = lo_out;
+    *reinterpret_cast<uint4 *>(hi_tile + off) = hi_out;
+    *reinterpret_cast<uint4 *>(lo_tile + off) = lo_out;
 }
 
 template <int F, bool PRE>
@@ -147,9 +150,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char *a_tiles = smem;                                   // [hi kb0][hi kb1][lo kb0][lo kb1]
-    unsigned char *b_tiles = smem + A_BYTES;                         // [(j*2 + part)*2 + kb]
-    float *w0s = reinterpret_cast<float *>(smem + A_BYTES + B_BYTES);   // [(F + 1)][512] layer-0 input rows + bias
-    uint64_t *h_ready = reinterpret_cast<uint64_t *>(smem + A_BYTES + B_BYTES + W0_FLOATS * 4);
+    // The half-0 epilogue (units 0..63 = K-block 0 of the next h) runs while the half-1 MMAs still read the
+    // current h, so K-block 0 alternates between its home tiles and `alt` by step parity; K-block 1 is written
+    // by the half-1 epilogue after every MMA of the step has retired and stays in place.
+    unsigned char *alt = smem + A_BYTES;                             // [hi kb0' | lo kb0']
+    unsigned char *b_tiles = smem + A_BYTES + ALT_BYTES;             // [(j*2 + part)*2 + kb]
+    // Overlap (ping-pong of K-block 0) is used by the pre-gate variant only; layer 0 keeps its input rows + bias in
+    // shared memory in the same 32 KB instead (reading them through L1 cost more than the overlap gained).
+    constexpr bool OVL = PRE;
+    float *w0s = reinterpret_cast<float *>(alt);                     // [(F + 1)][512], layer 0 only
+    uint64_t *h_ready = reinterpret_cast<uint64_t *>(smem + A_BYTES + ALT_BYTES + B_BYTES);
     uint64_t *acc_full = h_ready + 1;                 // [2]: one per 256-column half
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(h_ready + 3);
 
@@ -191,9 +201,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     if (warp == 1) {
         // ================= MMA issuer: one thread of the leader CTA drives both SMs =================
         if (rank == 0 && lane == 0) {
-            const uint32_t a0 = smem_u32(a_tiles), bb = smem_u32(b_tiles);
+            const uint32_t a0 = smem_u32(a_tiles), aalt = smem_u32(alt), bb = smem_u32(b_tiles);
             for (int s = 0; s < T; ++s) {
-                if (!mbar_wait_cluster(h_ready, s & 1, p.abort_flag)) break;
+                if (!mbar_wait(h_ready, s & 1, p.abort_flag)) break;
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");      // once per step: the peer CTA's h tiles are visible
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -203,18 +214,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                         const int pa = (combo == 0) ? 1 : 0;      // h_lo.U_hi, h_hi.U_lo, h_hi.U_hi
                         const int pb = (combo == 1) ? 1 : 0;
 #pragma unroll
-                        for (int kb = 0; kb < 2; ++kb)
+                        for (int kb = 0; kb < 2; ++kb) {
+                            // K-block 0 of h lives in its home tiles on even steps and in `alt` on odd steps
+                            const uint32_t abase = (kb == 1) ? a0 + (pa * 2 + 1) * TILE_BYTES
+                                                             : ((OVL && (s & 1)) ? aalt + pa * TILE_BYTES : a0 + (pa * 2) * TILE_BYTES);
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = make_desc(a0 + (pa * 2 + kb) * TILE_BYTES + ks * 32);
+                                const uint64_t ad = make_desc(abase + ks * 32);
                                 const uint64_t bd = make_desc(bb + ((j * 2 + pb) * 2 + kb) * TILE_BYTES + ks * 32);
                                 umma_f16_2sm(d, ad, bd, (combo | kb | ks) ? 1u : 0u);
                             }
+                        }
                     }
+                    if (OVL || j == 1) umma_commit_2sm(&acc_full[j]);     // OVL: half j's epilogue overlaps the MMAs of half j+1
                 }
-                // one commit for both halves: the epilogue rewrites the h tiles (A operand), which every MMA of
-                // the step reads, so it may only start when all of them have retired
-                umma_commit_2sm(&acc_full[0]);
             }
         }
     } else if (warp >= 2) {
@@ -244,7 +257,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
 #pragma unroll
                 for (int u = 0; u < 8; ++u) h8[u] = h0[8 * ch + u];
                 uint4 dh, dl;
-                store_h8(a_tiles, row, hlf, ch, h8, dh, dl);
+                store_h8(a_tiles + hlf * TILE_BYTES, a_tiles + (2 + hlf) * TILE_BYTES, row, ch, h8, dh, dl);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -274,7 +287,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 for (int i = 0; i < 4; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
             }
             float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf : nullptr;
-            ok = mbar_wait_cluster(&acc_full[0], s & 1, p.abort_flag);
+            // destination tiles of the next h: K-block 0 ping-pongs (home tiles on even steps, `alt` on odd ones)
+            unsigned char *hi_dst = (hlf == 1) ? a_tiles + TILE_BYTES : ((OVL && ((s + 1) & 1)) ? alt : a_tiles);
+            unsigned char *lo_dst = (hlf == 1) ? a_tiles + 3 * TILE_BYTES : ((OVL && ((s + 1) & 1)) ? alt + TILE_BYTES : a_tiles + 2 * TILE_BYTES);
+            ok = mbar_wait(&acc_full[OVL ? hlf : 1], s & 1, p.abort_flag);
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -324,7 +340,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                     }
                 }
                 uint4 ph, pl;
-                store_h8(a_tiles, row, hlf, ch, h8, ph, pl);
+                store_h8(hi_dst, lo_dst, row, ch, h8, ph, pl);
                 if (live) {
                     if (p.y16_hi != nullptr) {          // intermediate layer: fp16 hi/lo planes for the next projection
                         const size_t o = (size_t)b * p.y16_bs + (size_t)t * p.y16_ts + dir * UNITS + 64 * hlf + 8 * ch;
