@@ -62,14 +62,14 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     float *qs = attn + UNITS * RM;         // [256][32] folded query q' = W_mem . h
     float *wfc_s = qs + ENC_OUT * RM;      // [128*7]
     float *logit_s = wfc_s + UNITS * VOCAB;  // [32][8]
-    float *lp_s = logit_s + 32 * 8;        // [32] beam log-probs
-    float *nsc_s = lp_s + 32;              // [32] new scores
-    int *tok_s = reinterpret_cast<int *>(nsc_s + 32);   // [32]
-    int *fin_s = tok_s + 32;               // [32]
-    int *len_s = fin_s + 32;               // [32]
-    int *srow_s = len_s + 32;              // [32] source row for the reorder
-    int *nidx_s = srow_s + 32;             // [32] flat top-k index
-    int *first_s = nidx_s + 32;            // [32] greedy: first END step ; beam: per-snippet all-finished step
+    float *lp_s = logit_s + 64 * 8;        // [32] beam log-probs
+    float *nsc_s = lp_s + 64;              // [32] new scores
+    int *tok_s = reinterpret_cast<int *>(nsc_s + 64);   // [32]
+    int *fin_s = tok_s + 64;               // [32]
+    int *len_s = fin_s + 64;               // [32]
+    int *srow_s = len_s + 64;              // [32] source row for the reorder
+    int *nidx_s = srow_s + 64;             // [32] flat top-k index
+    int *first_s = nidx_s + 64;            // [32] greedy: first END step ; beam: per-snippet all-finished step
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int W = p.W, S = p.S, Tm = p.Tm;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     for (int i = tid; i < 640 * RM; i += THREADS) buf[i] = 0.0f;
     for (int i = tid; i < UNITS * RM; i += THREADS) { cs[i] = 0.0f; attn[i] = 0.0f; }
     for (int i = tid; i < UNITS * VOCAB; i += THREADS) wfc_s[i] = p.wfc[i];
-    if (tid < 32) {
+    if (tid < 64) {
         tok_s[tid] = TOKEN_START;
         int k = tid % W;
         lp_s[tid] = (k == 0) ? 0.0f : -INFINITY;
@@ -279,8 +279,8 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
         __syncthreads();
 
         // ---------------- phase 4: logits = attention . fc + b -----------------------------------------
-        if (tid < R * VOCAB) {
-            const int r = tid / VOCAB, v = tid % VOCAB;
+        for (int o = tid; o < R * VOCAB; o += THREADS) {
+            const int r = o / VOCAB, v = o % VOCAB;
             float a = p.bfc[v];
 #pragma unroll 8
             for (int k = 0; k < UNITS; ++k) a = fmaf(attn[k * RM + r], wfc_s[k * VOCAB + v], a);
@@ -355,6 +355,24 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
         }
         __syncthreads();
 
+        // ---------------- early exit (beam search): every beam of every snippet of this CTA has finished -----
+        // A finished beam can only continue with the end token at unchanged score, and top_k keeps the
+        // (already descending) order, so the remaining steps are known: scores = current log-probs,
+        // predicted id = end token, parent = identity (A.5).  Fill them and stop.
+        if (p.beam) {
+            bool all_done = true;
+            for (int s = 0; s < ns; ++s) all_done = all_done && (first_s[s] != S);
+            if (all_done) {
+                for (int o = tid; o < R * (S - 1 - t); o += THREADS) {
+                    const int row = o % R, tt = t + 1 + o / R;
+                    const int s = row / W, k = row % W;
+                    const size_t g = ((size_t)(s0 + s) * S + tt) * W + k;
+                    p.scores[g] = lp_s[row]; p.step_ids[g] = TOKEN_END; p.parent_ids[g] = k;
+                }
+                break;
+            }
+        }
+
         // ---------------- state hand-over to the next step (beam: gather by parent) ---------------------
         if (!p.beam) {
             for (int i = tid; i < UNITS * RM; i += THREADS) buf[i] = attn[i];
@@ -412,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 }
 
 template <int RM>
-constexpr size_t smem_floats() { return (size_t)640 * RM + 2 * UNITS * RM + ENC_OUT * RM + UNITS * VOCAB + 32 * 8 + 2 * 32 + 6 * 32; }
+constexpr size_t smem_floats() { return (size_t)640 * RM + 2 * UNITS * RM + ENC_OUT * RM + UNITS * VOCAB + 64 * 8 + 2 * 64 + 6 * 64; }
 
 template <int WT, int RM, int MINB>
 static int launch(const Params &p, cudaStream_t stream) {
@@ -434,7 +452,8 @@ int run(const Params &p, cudaStream_t stream) {
     // beam 1 / greedy: 16 rows per CTA and two CTAs per SM, so that one CTA's dense phases overlap the
     // other's HBM streaming; wider beams: 32 rows (all beams of a snippet stay in one CTA)
     if (p.W == 1) return launch<1, 16, 2>(p, stream);
-    if (p.W <= 5) return launch<5, 32, 1>(p, stream);
+    if (p.W == 5) return launch<5, 40, 1>(p, stream);      // 8 snippets x 5 beams: every warp owns a snippet in the attention pass
+    if (p.W < 5) return launch<5, 32, 1>(p, stream);
     return launch<9, 32, 1>(p, stream);
 }
 

@@ -106,6 +106,26 @@ def test_beam_matches_oracle(kind, W):
     np.testing.assert_allclose(sc[same], rsc[same], rtol=RTOL, atol=1e-4)
 
 
+@pytest.mark.parametrize("W", [1, 5])
+def test_beam_early_termination_matches_oracle(W):
+    """A large end-token bias makes every beam finish within a few steps: the kernel's early exit must
+    reproduce what tfa's dynamic_decode would have produced (T, ids, scores), also when other
+    snippets of the batch finish later."""
+    w = dict(W22)
+    b = w["decoder/fc/bias"].copy(); b[mr.TOKEN_END] += 2.5
+    w["decoder/fc/bias"] = b
+    n, L = 50, 20
+    x = inputs("joint", n, seed=11)
+    ids, sc = make("joint", weights=w).beam_search_prediction(x, W, L)
+    enc, mask = mr.encode_input(w, x, "joint")
+    rid, rsc = mr.beam_search(w, enc, mask, W, L)
+    assert rid.shape[1] < L - 1, "the bias should end decoding early"
+    assert ids.shape == rid.shape
+    same = np.array([np.array_equal(ids[i], rid[i]) for i in range(n)])
+    assert same.mean() >= 0.9, same.mean()
+    np.testing.assert_allclose(sc[same], rsc[same], rtol=1e-3, atol=2e-4)
+
+
 def test_beam_all_beams_internal_consistency():
     """predicted_ids must equal gather_tree(step_ids, parent_ids) recomputed by the oracle, exactly."""
     x = inputs("joint", 33, seed=9)
