@@ -101,7 +101,7 @@ int rvb_build_snippets(const void *d_signal, int sample_bytes, int64_t n_samples
  * Model handle -- replaces Basecaller.__init__ / load_weights
  * (basecaller.py:158-206; ravvent_performance_evaluator.py:89-107).
  * Supported: enc_units == dec_units == 128, encoder_depth 1..3,
- * decoder_depth 1, bilstm encoders, Luong attention, vocab 7.
+ * decoder_depth 1..2, bilstm encoders, Luong attention, vocab 7.
  * ------------------------------------------------------------------------ */
 int rvb_model_create(rvb_model_t **out, int device, int enc_units, int dec_units,
                      int encoder_depth, int decoder_depth, int vocab_size,

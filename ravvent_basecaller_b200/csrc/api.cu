@@ -66,6 +66,7 @@ struct rvb_model {
     bool rec_tc = false;                       // recurrences on tcgen05 (lstm_recurrent_tc.cu)
     uint16_t *d_bimg[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_w0[2] = {nullptr, nullptr};
+    float *d_wg1 = nullptr, *d_b1 = nullptr;
     float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
     // workspace for one wave
     size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
@@ -116,7 +117,7 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     if (enc_units != UNITS || dec_units != UNITS)
         return fail(RVB_ERR_ARG, "kernels are specialised for enc_units == dec_units == 128 (got %d, %d)", enc_units, dec_units);
     if (encoder_depth < 1 || encoder_depth > 3) return fail(RVB_ERR_ARG, "encoder_depth must be 1..3");
-    if (decoder_depth != 1) return fail(RVB_ERR_ARG, "decoder_depth must be 1 in this build");
+    if (decoder_depth < 1 || decoder_depth > 2) return fail(RVB_ERR_ARG, "decoder_depth must be 1 or 2");
     if (vocab_size != VOCAB) return fail(RVB_ERR_ARG, "vocab_size must be 7");
     if (input_kind < 0 || input_kind > 2) return fail(RVB_ERR_ARG, "bad input_kind");
     if (precision != RVB_PREC_FP32 && precision != RVB_PREC_BF16) return fail(RVB_ERR_ARG, "bad precision");
@@ -275,6 +276,22 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
                 for (int g = 0; g < 4; ++g)
                     wtok[((size_t)v * UNITS + u) * 4 + g] = Wd->data[(size_t)v * GATES + g * UNITS + u] + Bd->data[g * UNITS + u];
         RVB_CHECK(upload(m, &m->d_wg, wg));
+        if (m->dec_depth == 2) {
+            const HostTensor *W1, *U1, *B1;
+            RVB_CHECK(get_w(m, "decoder/cell1/kernel", UNITS, GATES, &W1));
+            RVB_CHECK(get_w(m, "decoder/cell1/recurrent_kernel", UNITS, GATES, &U1));
+            RVB_CHECK(get_w(m, "decoder/cell1/bias", GATES, -1, &B1));
+            std::vector<float> wg1((size_t)2 * UNITS * UNITS * 4), b1((size_t)UNITS * 4);
+            for (int k = 0; k < 2 * UNITS; ++k)
+                for (int u = 0; u < UNITS; ++u)
+                    for (int g = 0; g < 4; ++g)
+                        wg1[((size_t)k * UNITS + u) * 4 + g] = k < UNITS ? W1->data[(size_t)k * GATES + g * UNITS + u]
+                                                                         : U1->data[(size_t)(k - UNITS) * GATES + g * UNITS + u];
+            for (int u = 0; u < UNITS; ++u)
+                for (int g = 0; g < 4; ++g) b1[(size_t)u * 4 + g] = B1->data[g * UNITS + u];
+            RVB_CHECK(upload(m, &m->d_wg1, wg1));
+            RVB_CHECK(upload(m, &m->d_b1, b1));
+        }
         RVB_CHECK(upload(m, &m->d_wtok, wtok));
         RVB_CHECK(upload(m, &m->d_wmem, Wm->data));
         std::vector<float> wmT((size_t)UNITS * ENC_OUT);
@@ -443,7 +460,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
         dec::Params p{};
         p.wmemT = m->d_wmemT; p.values = m->enc_out; p.mask = m->mask;
-        p.wg = m->d_wg; p.wtok = m->d_wtok; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;
+        p.wg = m->d_wg; p.wtok = m->d_wtok; p.wg1 = m->d_wg1; p.b1 = m->d_b1; p.depth = m->dec_depth; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;
         p.B = nb; p.Tm = Tm; p.W = W; p.S = S; p.beam = beam ? 1 : 0;
         p.steps = d_steps;
         if (beam) {

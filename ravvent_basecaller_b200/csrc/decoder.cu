@@ -57,8 +57,8 @@ template <int WT, int RM, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     extern __shared__ __align__(16) float smem[];
     float *buf = smem;                       // [640][32]: 0..127 prev attention | 128..255 h | 256..511 context
-    float *cs = buf + 640 * RM;            // [128][32]
-    float *attn = cs + UNITS * RM;         // [128][32]
+    float *cs = buf + 640 * RM;            // [cell][128][RM] cell states of the (up to 2) stacked LSTM cells
+    float *attn = cs + 2 * UNITS * RM;     // [128][RM]
     float *qs = attn + UNITS * RM;         // [256][32] folded query q' = W_mem . h
     float *wfc_s = qs + ENC_OUT * RM;      // [128*7]
     float *logit_s = wfc_s + UNITS * VOCAB;  // [32][8]
@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     const int R = ns * W;
 
     for (int i = tid; i < 640 * RM; i += THREADS) buf[i] = 0.0f;
-    for (int i = tid; i < UNITS * RM; i += THREADS) { cs[i] = 0.0f; attn[i] = 0.0f; }
+    for (int i = tid; i < 2 * UNITS * RM; i += THREADS) cs[i] = 0.0f;
+    for (int i = tid; i < UNITS * RM; i += THREADS) attn[i] = 0.0f;
     for (int i = tid; i < UNITS * VOCAB; i += THREADS) wfc_s[i] = p.wfc[i];
     if (tid < 64) {
         tok_s[tid] = TOKEN_START;
@@ -93,20 +94,30 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     __syncthreads();
 
     const int u = tid & 127, half = tid >> 7;
+    // buf rows: [0,128) previous attention | [128*(j+1), 128*(j+2)) h of stacked cell j | then 256 rows of context.
+    // QROW = first row of the top cell's h (the attention query); [QROW, QROW+384) = [query | context] feeds phase 3.
+    const int depth = p.depth;
+    const int QROW = UNITS * depth;
     for (int t = 0; t < S; ++t) {
-        // ---------------- phase 1: LSTM cell on [one_hot(token) | prev attention] ----------------
-        {
+        // ---------------- phase 1: stacked LSTM cells (StackedRNNCells, basecaller.py:85-91) -------------
+        // cell 0 sees [one_hot(token) | prev attention], cell j > 0 sees the new h of cell j-1.
+        for (int cell = 0; cell < depth; ++cell) {
             constexpr int RH = RM / 2;
+            const float *wcell = cell == 0 ? p.wg : p.wg1;
+            const float *xin = buf + (size_t)cell * UNITS * RM;          // rows [128*cell, 128*cell + 256)
+            float *ccell = cs + (size_t)cell * UNITS * RM;
             float acc[RH][4];
 #pragma unroll
             for (int r = 0; r < RH; ++r) {
-                float4 w = __ldg(reinterpret_cast<const float4 *>(p.wtok + ((size_t)tok_s[half * RH + r] * UNITS + u) * 4));
+                const float4 w = cell == 0
+                    ? __ldg(reinterpret_cast<const float4 *>(p.wtok + ((size_t)tok_s[half * RH + r] * UNITS + u) * 4))
+                    : __ldg(reinterpret_cast<const float4 *>(p.b1 + (size_t)u * 4));
                 acc[r][0] = w.x; acc[r][1] = w.y; acc[r][2] = w.z; acc[r][3] = w.w;
             }
 #pragma unroll 8
             for (int k = 0; k < 2 * UNITS; ++k) {
-                const float4 w = __ldg(reinterpret_cast<const float4 *>(p.wg + ((size_t)k * UNITS + u) * 4));
-                const float4 *xr = reinterpret_cast<const float4 *>(buf + k * RM + half * RH);
+                const float4 w = __ldg(reinterpret_cast<const float4 *>(wcell + ((size_t)k * UNITS + u) * 4));
+                const float4 *xr = reinterpret_cast<const float4 *>(xin + k * RM + half * RH);
 #pragma unroll
                 for (int q = 0; q < RH / 4; ++q) {
                     const float4 x = xr[q];
@@ -120,18 +131,18 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
                     }
                 }
             }
-            __syncthreads();                 // every read of the old h rows is done
+            __syncthreads();                 // every read of this cell's old h rows is done
 #pragma unroll
             for (int r = 0; r < RH; ++r) {
                 int row = half * RH + r;
-                float c = cs[u * RM + row];
+                float c = ccell[u * RM + row];
                 float ig = fsig(acc[r][0]), fg = fsig(acc[r][1]), gg = ftanh(acc[r][2]), og = fsig(acc[r][3]);
                 c = fg * c + ig * gg;
-                cs[u * RM + row] = c;
-                buf[(UNITS + u) * RM + row] = og * ftanh(c);
+                ccell[u * RM + row] = c;
+                buf[((cell + 1) * UNITS + u) * RM + row] = og * ftanh(c);
             }
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---------------- phase 2a: q' = W_mem . h  (Luong score = keys.h = values.(W_mem.h)) ---------
         // Folding the memory layer into the query means only `values` is streamed per step (A.3).
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 #pragma unroll 8
             for (int k = 0; k < UNITS; ++k) {
                 const float w = __ldg(p.wmemT + (size_t)k * ENC_OUT + tid);
-                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RM);
+                const float4 *xr = reinterpret_cast<const float4 *>(buf + (QROW + k) * RM);
 #pragma unroll
                 for (int q = 0; q < RM / 4; ++q) {
                     const float4 x = xr[q];
@@ -249,8 +260,8 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
                     const float inv = (den[w] > 0.0f) ? 1.0f / den[w] : __int_as_float(0x7fc00000);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        buf[(2 * UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][e] * inv;
-                        buf[(3 * UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][4 + e] * inv;
+                        buf[(QROW + UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][e] * inv;
+                        buf[(QROW + 2 * UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][4 + e] * inv;
                     }
                 }
         }
@@ -265,7 +276,7 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 #pragma unroll 8
             for (int k = 0; k < 3 * UNITS; ++k) {
                 const float w = __ldg(p.watt + (size_t)k * UNITS + u);
-                const float4 *xr = reinterpret_cast<const float4 *>(buf + (UNITS + k) * RM + half * RH);
+                const float4 *xr = reinterpret_cast<const float4 *>(buf + (QROW + k) * RM + half * RH);
 #pragma unroll
                 for (int q = 0; q < RH / 4; ++q) {
                     const float4 x = xr[q];
@@ -378,20 +389,24 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
             for (int i = tid; i < UNITS * RM; i += THREADS) buf[i] = attn[i];
         } else {
             constexpr int NE = UNITS * RM / THREADS;
-            float hv[NE], cv[NE];
+            for (int cell = 0; cell < depth; ++cell) {
+                float *hcell = buf + (size_t)(cell + 1) * UNITS * RM;
+                float *ccell = cs + (size_t)cell * UNITS * RM;
+                float hv[NE], cv[NE];
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const int i = tid + e * THREADS, d = i / RM, r = i % RM, sr = srow_s[r];
-                hv[e] = buf[(UNITS + d) * RM + sr];
-                cv[e] = cs[d * RM + sr];
-                buf[d * RM + r] = attn[d * RM + sr];
-            }
-            __syncthreads();
+                for (int e = 0; e < NE; ++e) {
+                    const int i = tid + e * THREADS, d = i / RM, r = i % RM, sr = srow_s[r];
+                    hv[e] = hcell[d * RM + sr];
+                    cv[e] = ccell[d * RM + sr];
+                    if (cell == 0) buf[d * RM + r] = attn[d * RM + sr];
+                }
+                __syncthreads();
 #pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const int i = tid + e * THREADS, d = i / RM, r = i % RM;
-                buf[(UNITS + d) * RM + r] = hv[e];
-                cs[d * RM + r] = cv[e];
+                for (int e = 0; e < NE; ++e) {
+                    const int i = tid + e * THREADS, d = i / RM, r = i % RM;
+                    hcell[d * RM + r] = hv[e];
+                    ccell[d * RM + r] = cv[e];
+                }
             }
         }
         __syncthreads();
@@ -430,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 }
 
 template <int RM>
-constexpr size_t smem_floats() { return (size_t)640 * RM + 2 * UNITS * RM + ENC_OUT * RM + UNITS * VOCAB + 64 * 8 + 2 * 64 + 6 * 64; }
+constexpr size_t smem_floats() { return (size_t)640 * RM + 3 * UNITS * RM + ENC_OUT * RM + UNITS * VOCAB + 64 * 8 + 2 * 64 + 6 * 64; }
 
 template <int WT, int RM, int MINB>
 static int launch(const Params &p, cudaStream_t stream) {
@@ -449,6 +464,7 @@ int run(const Params &p, cudaStream_t stream) {
     if (p.B <= 0 || p.S <= 0) return RVB_OK;
     if (p.Tm > TMAX) return fail(RVB_ERR_ARG, "decoder: memory length %d > %d", p.Tm, TMAX);
     if (p.W < 1 || p.W > WMAX) return fail(RVB_ERR_ARG, "decoder: beam width must be in [1,%d]", WMAX);
+    if (p.depth < 1 || p.depth > 2) return fail(RVB_ERR_ARG, "decoder: depth must be 1 or 2");
     // beam 1 / greedy: 16 rows per CTA and two CTAs per SM, so that one CTA's dense phases overlap the
     // other's HBM streaming; wider beams: 32 rows (all beams of a snippet stay in one CTA)
     if (p.W == 1) return launch<1, 16, 2>(p, stream);

@@ -62,6 +62,9 @@ struct Params {
     const uint8_t *mask;    // [B,Tm]
     const float *wg;        // [256][128][4]  rows 0..127: kernel rows of the attention input, 128..255: recurrent kernel
     const float *wtok;      // [7][128][4]    kernel row of token v + bias
+    const float *wg1;       // [256][128][4]  second stacked cell: rows 0..127 kernel (input = h of cell 0), 128..255 recurrent
+    const float *b1;        // [128][4]       second stacked cell bias
+    int depth;              // decoder_depth: 1 or 2 stacked LSTM cells
     const float *watt;      // [384][128]
     const float *wfc;       // [128][7]
     const float *bfc;       // [7]

@@ -16,9 +16,9 @@ RTOL, ATOL = 1e-3, 2e-5
 W22 = mr.init_weights(22, random_bias=True)
 
 
-def make(kind, depth=2, wave=0, weights=None):
+def make(kind, depth=2, wave=0, weights=None, dec_depth=1):
     import ravvent_basecaller_b200 as rb
-    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, kind, 0., encoder_depth=depth, decoder_depth=1, wave_snippets=wave)
+    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, kind, 0., encoder_depth=depth, decoder_depth=dec_depth, wave_snippets=wave)
     bc.compile(optimizer=None)
     bc.load_weights(weights if weights is not None else W22)
     return bc
@@ -124,6 +124,30 @@ def test_beam_early_termination_matches_oracle(W):
     same = np.array([np.array_equal(ids[i], rid[i]) for i in range(n)])
     assert same.mean() >= 0.9, same.mean()
     np.testing.assert_allclose(sc[same], rsc[same], rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("enc_depth,W", [(3, 1), (3, 5), (2, 5)])
+def test_decoder_depth_2(enc_depth, W):
+    """(encoder_depth, decoder_depth) = (3,2) and (2,2): the other configurations of the shipped results
+    (accuracy_results_all.lambda.beam5.json:89,118): two stacked decoder LSTM cells."""
+    w = mr.init_weights(31, encoder_depth=enc_depth, decoder_depth=2, random_bias=True)
+    n, L = 40, 14
+    x = inputs("joint", n, seed=12)
+    bc = make("joint", depth=enc_depth, weights=w, dec_depth=2)
+    enc, mask = mr.encode_input(w, x, "joint", encoder_depth=enc_depth)
+    ids, sc = bc.beam_search_prediction(x, W, L)
+    rid, rsc = mr.beam_search(w, enc, mask, W, L, decoder_depth=2)
+    assert ids.shape == rid.shape
+    same = np.array([np.array_equal(ids[i], rid[i]) for i in range(n)])
+    assert same.mean() >= 0.9, same.mean()
+    np.testing.assert_allclose(sc[same], rsc[same], rtol=1e-3, atol=2e-4)
+    if W == 1:
+        gid, glog = bc.greedy_search_prediction(x, L)
+        rgid, rglog = mr.greedy_search(w, enc, mask, L, decoder_depth=2)
+        assert gid.shape == rgid.shape
+        ok = np.array([np.array_equal(gid[i], rgid[i]) for i in range(n)])
+        assert ok.mean() >= 0.9
+        np.testing.assert_allclose(glog[ok], rglog[ok], rtol=1e-3, atol=2e-4)
 
 
 def test_beam_all_beams_internal_consistency():
