@@ -89,13 +89,15 @@ int rvb_event_detect(const void *d_signal, int sample_bytes,
  * are already on the device (output of rvb_event_detect).
  *   d_raw_snips   [max_snippets,200,1] f32, d_event_snips [max_snippets,30,5] f32
  *   h_n_snippets  number of snippets produced (host, written after a stream sync)
+ *   d_raw_ranges  optional [max_snippets,2] int32: sample range [start,end) of each snippet in the read
+ *                 (what the reference uses to cut the label sequence, data_loader.py:101-102); may be NULL
  * ------------------------------------------------------------------------ */
 int rvb_build_snippets(const void *d_signal, int sample_bytes, int64_t n_samples,
                        const int32_t *d_ev_start, const int32_t *d_ev_length,
                        const double *d_ev_mean, const double *d_ev_stdv, int32_t n_events,
                        int64_t label_start, int64_t label_end, int32_t stride,
                        float *d_raw_snips, float *d_event_snips, int32_t max_snippets,
-                       int32_t *h_n_snippets, void *stream);
+                       int32_t *h_n_snippets, int32_t *d_raw_ranges, void *stream);
 
 /* ------------------------------------------------------------------------
  * Model handle -- replaces Basecaller.__init__ / load_weights

@@ -155,7 +155,7 @@ __global__ void window_kernel(const int *P, Scratch *sc, int stride, int max_w, 
 template <typename T>
 __global__ void fill_kernel(const T *raw, long long n, const int32_t *ev_start, const int32_t *ev_len, const double *ev_mean,
                             const double *ev_stdv, const int *win_end, const Scratch *sc, int stride, int max_w,
-                            float *raw_out, float *ev_out) {
+                            float *raw_out, float *ev_out, int32_t *ranges_out) {
     const int w = blockIdx.x;
     const int nw = min(sc->n_windows, max_w);
     if (w >= nw) return;
@@ -163,6 +163,7 @@ __global__ void fill_kernel(const T *raw, long long n, const int32_t *ev_start, 
     const int first = w * stride, end = win_end[w];
     auto mstart = [&](int j) -> long long { return j == 0 ? sc->first_start : (long long)(uint32_t)ev_start[k0 + j]; };
     const long long r0 = mstart(first), r1 = mstart(end - 1);      // raw span excludes the last event (:48-51)
+    if (ranges_out != nullptr && threadIdx.x == 0) { ranges_out[2 * w] = (int32_t)r0; ranges_out[2 * w + 1] = (int32_t)r1; }
     for (int i = threadIdx.x; i < MAX_RAW; i += blockDim.x) {
         const long long idx = r0 + i;
         float v = 0.0f;
@@ -191,7 +192,7 @@ extern "C" int rvb_build_snippets(const void *d_signal, int sample_bytes, int64_
                                   const int32_t *d_ev_length, const double *d_ev_mean, const double *d_ev_stdv,
                                   int32_t n_events, int64_t label_start, int64_t label_end, int32_t stride,
                                   float *d_raw_snips, float *d_event_snips, int32_t max_snippets, int32_t *h_n_snippets,
-                                  void *stream_) {
+                                  int32_t *d_raw_ranges, void *stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!h_n_snippets) return fail(RVB_ERR_ARG, "build_snippets: null count output");
     *h_n_snippets = 0;
@@ -219,10 +220,10 @@ extern "C" int rvb_build_snippets(const void *d_signal, int sample_bytes, int64_
         if (fill_w > 0) {
             if (sample_bytes == 4)
                 snip::fill_kernel<int32_t><<<fill_w, 128, 0, stream>>>(reinterpret_cast<const int32_t *>(d_signal), n_samples, d_ev_start, d_ev_length,
-                                                                       d_ev_mean, d_ev_stdv, win_end, sc, stride, fill_w, d_raw_snips, d_event_snips);
+                                                                       d_ev_mean, d_ev_stdv, win_end, sc, stride, fill_w, d_raw_snips, d_event_snips, d_raw_ranges);
             else
                 snip::fill_kernel<int16_t><<<fill_w, 128, 0, stream>>>(reinterpret_cast<const int16_t *>(d_signal), n_samples, d_ev_start, d_ev_length,
-                                                                       d_ev_mean, d_ev_stdv, win_end, sc, stride, fill_w, d_raw_snips, d_event_snips);
+                                                                       d_ev_mean, d_ev_stdv, win_end, sc, stride, fill_w, d_raw_snips, d_event_snips, d_raw_ranges);
         }
         count_launch(3);
     }

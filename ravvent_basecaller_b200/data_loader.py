@@ -56,7 +56,8 @@ def calc_prob_logits_beam_search_scores(beam_scores):
     return np.exp(s - prev)
 
 
-def load_data_from_signal(raw, label_start=None, label_end=None, stride=6, device=None, detector=None):
+def load_data_from_signal(raw, label_start=None, label_end=None, stride=6, device=None, detector=None,
+                          return_ranges=False):
     """Inference half of ``load_data_from_single_signal_label`` (data_loader.py:113-126) for one read that
     is already in memory: GPU event detection (K1), then the GPU snippet builder.
 
@@ -83,8 +84,55 @@ def load_data_from_signal(raw, label_start=None, label_end=None, stride=6, devic
         raw_s = torch.zeros((cap, MAX_RAW_LEN, 1), dtype=torch.float32, device=dev)
         ev_s = torch.zeros((cap, MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
         cnt = C.c_int32(0)
+        ranges = torch.zeros((cap, 2), dtype=torch.int32, device=dev) if return_ranges else None
         _lib.check(_lib.lib.rvb_build_snippets(
             sig.data_ptr(), sig.element_size(), n, ev["start"].data_ptr(), ev["length"].data_ptr(),
             ev["mean"].data_ptr(), ev["stdv"].data_ptr(), n_ev, lab0, lab1, int(stride),
-            raw_s.data_ptr(), ev_s.data_ptr(), cap, C.byref(cnt), torch.cuda.current_stream(dev).cuda_stream))
+            raw_s.data_ptr(), ev_s.data_ptr(), cap, C.byref(cnt), None if ranges is None else ranges.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream))
+    if return_ranges:
+        return raw_s[:cnt.value], ev_s[:cnt.value], ranges[:cnt.value]
     return raw_s[:cnt.value], ev_s[:cnt.value]
+
+
+def _label_tokens(raw_ranges, nuc_raw_ranges, nuc_reference_symbols):
+    """Target token rows of the snippets (data_loader.py:53-61, 101-108, 123-124): the labelled bases whose
+    sample ranges intersect each snippet's raw range, wrapped in '$' ... '^', tokenised char-level and
+    post-padded with the padding token to the longest row (int64)."""
+    nuc_raw_ranges = np.asarray(nuc_raw_ranges).astype(np.int64)
+    lens = nuc_raw_ranges[:, 1] - nuc_raw_ranges[:, 0]
+    edges = nuc_raw_ranges[0, 0] + np.concatenate(([0], np.cumsum(lens)))      # id k covers [edges[k], edges[k+1])
+    total = int(edges[-1])
+    rows = []
+    for r0, r1 in np.asarray(raw_ranges, dtype=np.int64):
+        r1 = min(int(r1), total)
+        if r1 <= r0:
+            ids = np.zeros(0, dtype=np.int64)
+        else:
+            first = int(np.searchsorted(edges, r0, side="right") - 1)
+            last = int(np.searchsorted(edges, r1 - 1, side="right") - 1)
+            ids = np.arange(first, last + 1)                                   # first == -1 reproduces the reference's quirk
+        text = '$' + ''.join(np.asarray(nuc_reference_symbols, dtype=object)[ids]) + '^'
+        rows.append(nuc_tk.texts_to_sequences([text])[0])
+    width = max((len(r) for r in rows), default=0)
+    out = np.full((len(rows), width), NUC_TOKEN_PAD, dtype=np.int64)
+    for i, r in enumerate(rows):
+        out[i, :len(r)] = r
+    return out
+
+
+def load_data_from_single_signal_label(signal_path, label_path, stride, as_numpy=True, device=None):
+    """Drop-in for data_loader.load_data_from_single_signal_label (data_loader.py:113-126): Chiron-style
+    `.signal` (whitespace-separated integers) + `.label` (`start end base` rows) ->
+    (raw_snippets [Ns,200,1] f32, event_snippets [Ns,30,5] f32, nuc_tk_snippets [Ns,L] int64).
+    Event detection and snippet building run on the GPU; the label side is host numpy like the reference."""
+    raw = np.loadtxt(signal_path, dtype=int)
+    label = np.loadtxt(label_path, dtype=object, ndmin=2)
+    nuc_raw_ranges = label[:, :2].astype(int)
+    nuc_reference_symbols = label[:, 2]
+    rs, es, ranges = load_data_from_signal(raw, int(nuc_raw_ranges[0, 0]), int(nuc_raw_ranges[-1, 1]), stride,
+                                           device=device, return_ranges=True)
+    tokens = _label_tokens(ranges.cpu().numpy(), nuc_raw_ranges, nuc_reference_symbols)
+    if as_numpy:
+        return rs.cpu().numpy(), es.cpu().numpy(), tokens
+    return rs, es, tokens

@@ -55,3 +55,22 @@ def test_short_and_empty_reads():
         raw = event_ref.synth_read(np.random.default_rng(n), n) if n else np.zeros(0, np.int32)
         rs, es = dl.load_data_from_signal(raw)
         assert rs.shape[0] == 0 and es.shape[0] == 0
+
+
+@pytest.mark.parametrize("k", [0, 1, 2])
+def test_signal_label_files_match_reference_loader(k, tmp_path):
+    """§8f-3: the on-disk entry point (Chiron .signal / .label) against the reference's own
+    load_data_from_single_signal_label, including the target token rows."""
+    from ravvent_basecaller_b200 import data_loader as dl
+    g = np.load(GOLDEN / "snippets_golden.npz")
+    raw = g[f"raw_{k}"].astype(np.int64)
+    stride = int(g[f"par_{k}"][2])
+    sp, lp = tmp_path / "r.signal", tmp_path / "r.label"
+    np.savetxt(sp, raw.reshape(1, -1), fmt="%d")
+    with open(lp, "w") as f:
+        for (a, b), c in zip(g[f"label_ranges_{k}"], g[f"label_syms_{k}"]):
+            f.write(f"{a} {b} {chr(c)}\n")
+    rs, es, tk = dl.load_data_from_single_signal_label(str(sp), str(lp), stride)
+    assert rs.shape == g[f"raw_snips_{k}"].shape and es.shape == g[f"event_snips_{k}"].shape
+    assert _ulp_close(rs, g[f"raw_snips_{k}"]) and _ulp_close(es, g[f"event_snips_{k}"])
+    assert tk.dtype == np.int64 and np.array_equal(tk, g[f"tokens_{k}"])

@@ -35,14 +35,17 @@ def _stub_tf_keras():
         tail = seqs[0].shape[1:] if seqs else ()
         out = np.full((len(seqs), maxlen) + tuple(tail), value, dtype=dtype)
         for i, s in enumerate(seqs):
-            assert padding == "post" and truncating == "post"
+            assert padding == "post" and (truncating == "post" or len(s) <= maxlen)
             s = s[:maxlen]
             out[i, :len(s)] = s
         return out
 
-    class Tokenizer:
+    class Tokenizer:                       # char_level=True, lower=True, filters='' as configured at data_loader.py:20
         def __init__(self, **kw):
             self.word_index, self.index_word = {}, {}
+
+        def texts_to_sequences(self, texts):
+            return [[self.word_index[c] for c in t.lower() if c in self.word_index] for t in texts]
 
     tf = types.ModuleType("tensorflow")
     tf.keras = types.ModuleType("tensorflow.keras")
@@ -111,6 +114,19 @@ def snippets_golden(out: Path):
         blob[f"par_{k}"] = np.array([lab0, lab1, stride], dtype=np.int64)
         blob[f"raw_snips_{k}"] = dl.pad_input_snippets(raw_s, dl.MAX_RAW_LEN)
         blob[f"event_snips_{k}"] = dl.pad_input_snippets(ev_s, dl.MAX_EVENT_LEN)
+        # the on-disk entry point with the same read: also pins the target token rows
+        import tempfile, os
+        with tempfile.TemporaryDirectory() as td:
+            sp, lp = os.path.join(td, "r.signal"), os.path.join(td, "r.label")
+            np.savetxt(sp, raw.reshape(1, -1), fmt="%d")
+            with open(lp, "w") as f:
+                for (a, b), c in zip(ranges, syms):
+                    f.write(f"{a} {b} {c}\n")
+            r3, e3, tk = dl.load_data_from_single_signal_label(sp, lp, stride)
+        assert np.array_equal(r3, blob[f"raw_snips_{k}"])
+        blob[f"tokens_{k}"] = tk.astype(np.int64)
+        blob[f"label_ranges_{k}"] = ranges.astype(np.int64)
+        blob[f"label_syms_{k}"] = np.array([ord(c) for c in syms], dtype=np.uint8)
         blob[f"raw_lens_{k}"] = np.array([len(s) for s in raw_s], dtype=np.int64)
         blob[f"event_lens_{k}"] = np.array([len(s) for s in ev_s], dtype=np.int64)
         print(f"snippet case {k}: n={n} -> {len(raw_s)} snippets, raw len {blob[f'raw_lens_{k}'].min()}-"
