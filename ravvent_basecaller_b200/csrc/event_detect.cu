@@ -19,6 +19,9 @@
 //     bit-for-bit, otherwise re-runs that sub-segment from the true state.  The
 //     result is therefore exactly the sequential one, for any `warmup`.
 //   * accepted boundaries -> events; per-event sums are exact int64 range sums.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace rvb {
@@ -60,6 +63,7 @@ struct Params {
     const long long *ev_off;
     const int32_t *chunk_read;
     const int32_t *chunk_idx;
+    const int32_t *chunk_prev;   // ticket of the previous chunk of the same read (-1 for the first)
     int n_chunks;
     int w1, w2;
     double thr1, thr2, ph;
@@ -278,7 +282,8 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
         Pair cur; uint32_t ev_st = 0; long long m_st = 0; int count = 0;
         if (ci == 0) { det_reset(cur.s); det_reset(cur.l); pair_normalise(cur, 0, w2); }
         else {
-            volatile Chain *prev = p.chain + (c - 1);
+            const int cp = p.chunk_prev[c];
+            volatile Chain *prev = p.chain + cp;
             unsigned spins = 0; bool ok = true;
             while (true) {
                 int f;
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
                 __nanosleep(40);
             }
             if (!ok) { atomicExch(p.status, RVB_ERR_INTERNAL); s_abort = 1; }
-            const Chain *pc = p.chain + (c - 1);
+            const Chain *pc = p.chain + cp;
             cur = pc->st; ev_st = pc->ev_st; m_st = pc->m_st; count = pc->ev_count;
         }
         s_evst0 = ev_st; s_mst0 = m_st; s_count0 = count;
@@ -390,7 +395,7 @@ constexpr size_t SMEM_BYTES = sizeof(double) * 2 * TS_CAP + sizeof(Pair) * 2 * N
                               sizeof(int) * CH + sizeof(uint32_t) * NSUB;
 
 struct Layout {
-    size_t ticket, chain, chunk_read, chunk_idx, read_off, ev_off, total;
+    size_t ticket, chain, chunk_read, chunk_idx, chunk_prev, read_off, ev_off, total;
     long long n_chunks;
 };
 
@@ -408,6 +413,7 @@ static Layout make_layout(const int64_t *h_read_off, int32_t n_reads) {
     L.chain = off; off = al(off + sizeof(Chain) * (size_t)nc);
     L.chunk_read = off; off = al(off + sizeof(int32_t) * (size_t)nc);
     L.chunk_idx = off; off = al(off + sizeof(int32_t) * (size_t)nc);
+    L.chunk_prev = off; off = al(off + sizeof(int32_t) * (size_t)nc);
     L.read_off = off; off = al(off + sizeof(int64_t) * (size_t)(n_reads + 1));
     L.ev_off = off; off = al(off + sizeof(int64_t) * (size_t)(n_reads + 1));
     L.total = off;
@@ -447,19 +453,31 @@ extern "C" int rvb_event_detect(const void *d_signal, int sample_bytes, const in
     char *ws = reinterpret_cast<char *>(d_workspace);
     RVB_CUDA(cudaMemsetAsync(d_ev_count, 0, sizeof(int32_t) * n_reads, stream));
     if (L.n_chunks == 0) { RVB_CUDA(cudaStreamSynchronize(stream)); return RVB_OK; }
-    // host-side chunk table (tiny): chunk -> (read, index in read), ordered so that a chunk only ever
-    // waits on a lower ticket
-    int32_t *h_tab = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)L.n_chunks);
+    // host-side chunk table (tiny): ticket -> (read, chunk index in read).  Tickets are handed out in table
+    // order, so a chunk only ever waits on a lower ticket (forward progress).  The table is ordered by LAYER
+    // (chunk 0 of every read, then chunk 1 of every read, ...): with many reads in the batch the predecessor of a
+    // chunk finished a whole round of CTAs earlier, so the read-internal chain never ripples.  `chain` is indexed
+    // by ticket; chunk (r,i) finds its predecessor (r,i-1) through chunk_prev.
+    int32_t *h_tab = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)L.n_chunks);
     if (!h_tab) return fail(RVB_ERR_INTERNAL, "out of host memory");
-    long long k = 0;
-    for (int r = 0; r < n_reads; ++r) {
-        long long n = h_read_offsets[r + 1] - h_read_offsets[r];
-        long long nc = (n + ed::CH - 1) / ed::CH;
-        for (long long i = 0; i < nc; ++i, ++k) { h_tab[k] = r; h_tab[L.n_chunks + k] = (int32_t)i; }
+    {
+        long long max_nc = 0;
+        for (int r = 0; r < n_reads; ++r) max_nc = std::max(max_nc, (long long)((h_read_offsets[r + 1] - h_read_offsets[r] + ed::CH - 1) / ed::CH));
+        std::vector<int32_t> last_ticket((size_t)n_reads, -1);
+        long long k = 0;
+        for (long long i = 0; i < max_nc; ++i)
+            for (int r = 0; r < n_reads; ++r) {
+                const long long nc = (h_read_offsets[r + 1] - h_read_offsets[r] + ed::CH - 1) / ed::CH;
+                if (i >= nc) continue;
+                h_tab[k] = r; h_tab[L.n_chunks + k] = (int32_t)i; h_tab[2 * L.n_chunks + k] = last_ticket[r];
+                last_ticket[r] = (int32_t)k;
+                ++k;
+            }
     }
     cudaError_t e = cudaMemsetAsync(ws + L.ticket, 0, L.chunk_read - L.ticket, stream);   // ticket, status, chain flags
     if (e == cudaSuccess) e = cudaMemcpyAsync(ws + L.chunk_read, h_tab, sizeof(int32_t) * L.n_chunks, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ws + L.chunk_idx, h_tab + L.n_chunks, sizeof(int32_t) * L.n_chunks, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ws + L.chunk_prev, h_tab + 2 * L.n_chunks, sizeof(int32_t) * L.n_chunks, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ws + L.read_off, h_read_offsets, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ws + L.ev_off, h_event_offsets, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);     // pageable staging buffers are ours to free after this
@@ -472,6 +490,7 @@ extern "C" int rvb_event_detect(const void *d_signal, int sample_bytes, const in
     p.ev_off = reinterpret_cast<const long long *>(ws + L.ev_off);
     p.chunk_read = reinterpret_cast<const int32_t *>(ws + L.chunk_read);
     p.chunk_idx = reinterpret_cast<const int32_t *>(ws + L.chunk_idx);
+    p.chunk_prev = reinterpret_cast<const int32_t *>(ws + L.chunk_prev);
     p.n_chunks = (int)L.n_chunks;
     p.w1 = w1; p.w2 = w2; p.thr1 = thr1; p.thr2 = thr2; p.ph = peak_height; p.H = warmup;
     p.ev_start = d_ev_start; p.ev_length = d_ev_length; p.ev_mean = d_ev_mean; p.ev_stdv = d_ev_stdv;
