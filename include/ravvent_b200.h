@@ -43,8 +43,8 @@ extern "C" {
 #define RVB_INPUT_EVENT    1
 #define RVB_INPUT_JOINT    2
 
-#define RVB_PREC_FP32      0   /* fp32 storage; projections 3xTF32 on tcgen05, recurrences FFMA */
-#define RVB_PREC_BF16      1   /* bf16 operands on tcgen05, fp32 accumulate / cell state        */
+#define RVB_PREC_FP32      0   /* parity mode: split-precision (3-pass) tensor-core products, fp32-accurate     */
+#define RVB_PREC_BF16      1   /* reduced mode: single 16-bit pass, fp32 accumulate / cell state, fp16 attention memory */
 
 typedef struct rvb_model rvb_model_t;
 

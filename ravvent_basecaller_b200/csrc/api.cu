@@ -74,6 +74,7 @@ struct rvb_model {
     float *G_raw = nullptr, *G_ev = nullptr;
     float *st[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [encoder][ping-pong]
     float *enc_out = nullptr, *keys = nullptr;
+    uint16_t *enc_out16 = nullptr;             // fp16 copy of enc_out (reduced-precision mode only)
     uint8_t *mask = nullptr;
     int32_t *step_ids = nullptr, *parent_ids = nullptr;
     // host-variant device buffers
@@ -336,6 +337,7 @@ static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
     if ((size_t)Tm > m->ws_tm) {
         dfree(m, m->enc_out); dfree(m, m->mask);
         RVB_CHECK(dmalloc(m, &m->enc_out, wv * Tm * ENC_OUT));
+        if (m->precision == RVB_PREC_BF16 && m->rec_tc) { dfree(m, m->enc_out16); RVB_CHECK(dmalloc(m, &m->enc_out16, wv * Tm * ENC_OUT)); }
         RVB_CHECK(dmalloc(m, &m->mask, wv * Tm));
         m->ws_tm = Tm;
     }
@@ -370,7 +372,8 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
         p.y_bs = (long long)Tm * ENC_OUT; p.y_ts = ENC_OUT;
         p.y16_hi = last ? nullptr : pl_hi; p.y16_lo = last ? nullptr : pl_lo;
         p.y16_bs = ENC_OUT; p.y16_ts = (long long)nb * ENC_OUT;
-        p.B = nb; p.T = T; p.abort_flag = m->d_abort;
+        p.yv16 = (last && m->enc_out16 != nullptr && out == m->enc_out) ? m->enc_out16 + (size_t)t_off * ENC_OUT : nullptr;
+        p.B = nb; p.T = T; p.abort_flag = m->d_abort; p.precision = m->precision;
         if (l > 0) {
             const uint16_t *a_hi = reinterpret_cast<const uint16_t *>(yb[(l - 1) & 1]);
             RVB_CHECK(gemm::run_tc_f16(a_hi, a_hi + (size_t)nb * T * ENC_OUT, m->d_phi16[e][l], m->d_plo16[e][l], m->d_pb[e][l], G,
@@ -459,7 +462,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
         dec::Params p{};
-        p.wmemT = m->d_wmemT; p.values = m->enc_out; p.mask = m->mask;
+        p.wmemT = m->d_wmemT; p.values = m->enc_out; p.values16 = m->enc_out16; p.mask = m->mask;
         p.wg = m->d_wg; p.wtok = m->d_wtok; p.wg1 = m->d_wg1; p.b1 = m->d_b1; p.depth = m->dec_depth; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;
         p.B = nb; p.Tm = Tm; p.W = W; p.S = S; p.beam = beam ? 1 : 0;
         p.steps = d_steps;

@@ -12,6 +12,8 @@
 // one read of that snippet's keys/values per step (tfa tile_batch would replicate
 // them beam_width times).  Recurrent state (h, c, attention) never leaves shared
 // memory; the beam reorder is a shared-memory gather by parent index.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace rvb {
@@ -53,7 +55,41 @@ __device__ __forceinline__ void warp_topk(float c0, float c1, int n_cand, int W,
     }
 }
 
-template <int WT, int RM, int MINB>
+// One memory row as seen by a lane: 8 of the 256 columns.
+//   fp32 memory: columns 4*lane..+3 and 128+4*lane..+3 (two 128-bit loads, each coalesced across the warp)
+//   fp16 memory (reduced-precision mode): columns 8*lane..+7 (one 128-bit load)
+template <bool VH> struct MemRow;
+template <> struct MemRow<false> {
+    float4 a, b;
+    __device__ __forceinline__ void zero() { a = b = make_float4(0, 0, 0, 0); }
+    __device__ __forceinline__ void load(const void *base, size_t row, int lane) {
+        const float *vp = reinterpret_cast<const float *>(base) + row * ENC_OUT + 4 * lane;
+        a = __ldg(reinterpret_cast<const float4 *>(vp));
+        b = __ldg(reinterpret_cast<const float4 *>(vp + UNITS));
+    }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ static __forceinline__ int col(int lane, int e) { return e < 4 ? 4 * lane + e : UNITS + 4 * lane + (e - 4); }
+};
+template <> struct MemRow<true> {
+    uint4 r;
+    __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+    __device__ __forceinline__ void load(const void *base, size_t row, int lane) {
+        r = __ldg(reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(base) + row * ENC_OUT + 8 * lane));
+    }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    __device__ static __forceinline__ int col(int lane, int e) { return 8 * lane + e; }
+};
+
+template <int WT, int RM, int MINB, bool VH>
 __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
     extern __shared__ __align__(16) float smem[];
     float *buf = smem;                       // [640][32]: 0..127 prev attention | 128..255 h | 256..511 context
@@ -169,10 +205,11 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 
         // ---------------- phase 2b: masked softmax(values.q') and context in ONE pass over values -----
         // One warp per snippet, online softmax (running max / sum), all beams of the snippet share the
-        // stream.  Lane owns columns 4*lane..+3 and 128+4*lane..+3; rows are software-pipelined in
-        // groups of 4 (eight 128-bit loads in flight per lane, next group prefetched).
+        // stream.  A lane owns 8 of the 256 columns (MemRow); rows are software-pipelined in groups of 4
+        // with the next group prefetched.
         for (int s = wid; s < ns; s += THREADS / 32) {
             const size_t bm = (size_t)(s0 + s) * Tm;
+            const void *vmem = VH ? reinterpret_cast<const void *>(p.values16) : reinterpret_cast<const void *>(p.values);
             unsigned mbits = 0;                                   // validity of rows 8*lane .. 8*lane+7
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -184,25 +221,17 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
             for (int w = 0; w < WT; ++w) {
                 mx[w] = -INFINITY; den[w] = 0.0f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { acc[w][e] = 0.0f; q[w][e] = 0.0f; }
-                if (w < W) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        q[w][e] = qs[(4 * lane + e) * RM + s * W + w];
-                        q[w][4 + e] = qs[(UNITS + 4 * lane + e) * RM + s * W + w];
-                    }
+                for (int e = 0; e < 8; ++e) {
+                    acc[w][e] = 0.0f;
+                    q[w][e] = (w < W) ? qs[MemRow<VH>::col(lane, e) * RM + s * W + w] : 0.0f;
                 }
             }
-            const float *vbase = p.values + bm * ENC_OUT + 4 * lane;
-            float4 cur[8], nxt[8];
+            MemRow<VH> cur[4], nxt[4];
             unsigned vb_cur = __shfl_sync(0xffffffffu, mbits, 0) & 0xFu, vb_nxt = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                cur[2 * j] = cur[2 * j + 1] = make_float4(0, 0, 0, 0);
-                if ((vb_cur >> j) & 1u) {
-                    cur[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT));
-                    cur[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT + UNITS));
-                }
+                cur[j].zero();
+                if ((vb_cur >> j) & 1u) cur[j].load(vmem, bm + j, lane);
             }
             for (int t0 = 0; t0 < Tm; t0 += 4) {
                 const int t1 = t0 + 4;
@@ -210,22 +239,22 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
                 if (t1 < Tm) vb_nxt = (__shfl_sync(0xffffffffu, mbits, t1 >> 3) >> (t1 & 7)) & 0xFu;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    nxt[2 * j] = nxt[2 * j + 1] = make_float4(0, 0, 0, 0);
-                    if ((vb_nxt >> j) & 1u) {
-                        nxt[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT));
-                        nxt[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT + UNITS));
-                    }
+                    nxt[j].zero();
+                    if ((vb_nxt >> j) & 1u) nxt[j].load(vmem, bm + t1 + j, lane);
                 }
                 if (vb_cur != 0) {
+                    float vv[4][8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cur[j].unpack(vv[j]);
 #pragma unroll
                     for (int w = 0; w < WT; ++w)
                         if (w < W) {
                             float sj[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float4 a = cur[2 * j], b = cur[2 * j + 1];
-                                float d = a.x * q[w][0] + a.y * q[w][1] + a.z * q[w][2] + a.w * q[w][3] +
-                                          b.x * q[w][4] + b.y * q[w][5] + b.z * q[w][6] + b.w * q[w][7];
+                                float d = vv[j][0] * q[w][0];
+#pragma unroll
+                                for (int e = 1; e < 8; ++e) d = fmaf(vv[j][e], q[w][e], d);
 #pragma unroll
                                 for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
                                 sj[j] = ((vb_cur >> j) & 1u) ? d : -INFINITY;
@@ -240,17 +269,13 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) acc[w][e] *= scale;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float4 a = cur[2 * j], b = cur[2 * j + 1];
-                                acc[w][0] = fmaf(pj[j], a.x, acc[w][0]); acc[w][1] = fmaf(pj[j], a.y, acc[w][1]);
-                                acc[w][2] = fmaf(pj[j], a.z, acc[w][2]); acc[w][3] = fmaf(pj[j], a.w, acc[w][3]);
-                                acc[w][4] = fmaf(pj[j], b.x, acc[w][4]); acc[w][5] = fmaf(pj[j], b.y, acc[w][5]);
-                                acc[w][6] = fmaf(pj[j], b.z, acc[w][6]); acc[w][7] = fmaf(pj[j], b.w, acc[w][7]);
-                            }
+                            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) acc[w][e] = fmaf(pj[j], vv[j][e], acc[w][e]);
                         }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+                for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
                 vb_cur = vb_nxt;
             }
 #pragma unroll
@@ -259,10 +284,8 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
                     // every position masked: tfa's softmax over all -inf yields NaN; keep that contract
                     const float inv = (den[w] > 0.0f) ? 1.0f / den[w] : __int_as_float(0x7fc00000);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        buf[(QROW + UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][e] * inv;
-                        buf[(QROW + 2 * UNITS + 4 * lane + e) * RM + s * W + w] = acc[w][4 + e] * inv;
-                    }
+                    for (int e = 0; e < 8; ++e)
+                        buf[(QROW + UNITS + MemRow<VH>::col(lane, e)) * RM + s * W + w] = acc[w][e] * inv;
                 }
         }
         __syncthreads();
@@ -447,17 +470,23 @@ __global__ void __launch_bounds__(THREADS, MINB) decoder_kernel(Params p) {
 template <int RM>
 constexpr size_t smem_floats() { return (size_t)640 * RM + 3 * UNITS * RM + ENC_OUT * RM + UNITS * VOCAB + 64 * 8 + 2 * 64 + 6 * 64; }
 
-template <int WT, int RM, int MINB>
-static int launch(const Params &p, cudaStream_t stream) {
+template <int WT, int RM, int MINB, bool VH>
+static int launch_v(const Params &p, cudaStream_t stream) {
     const size_t smem = smem_floats<RM>() * sizeof(float);
-    RVB_CUDA(cudaFuncSetAttribute(decoder_kernel<WT, RM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RVB_CUDA(cudaFuncSetAttribute(decoder_kernel<WT, RM, MINB, VH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int SN = RM / p.W;
     dim3 grid((unsigned)((p.B + SN - 1) / SN));
     { ProfScope ps(KK_DECODER, stream);
-      decoder_kernel<WT, RM, MINB><<<grid, THREADS, smem, stream>>>(p); }
+      decoder_kernel<WT, RM, MINB, VH><<<grid, THREADS, smem, stream>>>(p); }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;
+}
+
+// values16 != nullptr selects the fp16 attention memory (reduced-precision mode)
+template <int WT, int RM, int MINB>
+static int launch(const Params &p, cudaStream_t stream) {
+    return p.values16 != nullptr ? launch_v<WT, RM, MINB, true>(p, stream) : launch_v<WT, RM, MINB, false>(p, stream);
 }
 
 int run(const Params &p, cudaStream_t stream) {

@@ -32,7 +32,9 @@ struct Params {
     long long y_bs, y_ts;
     uint16_t *y16_hi, *y16_lo;  // optional fp16 hi / lo planes of the same logical tensor (input of the next K2)
     long long y16_bs, y16_ts;
+    uint16_t *yv16;             // optional fp16 copy of y with the same (y_bs, y_ts) element strides (decoder memory, reduced-precision mode)
     int B, T;
+    int precision;              // RVB_PREC_FP32: 3 split passes, RVB_PREC_BF16: single 16-bit pass
     int *abort_flag;
 };
 int run(int feat, const Params &p, cudaStream_t stream);
@@ -59,6 +61,7 @@ namespace dec {     // K4 + K5, decoder.cu
 struct Params {
     const float *wmemT;     // [128][256] transposed Luong memory layer (keys are never materialised)
     const float *values;    // [B,Tm,256]
+    const uint16_t *values16;   // optional fp16 copy of values (reduced-precision mode): halves the decode-time HBM traffic
     const uint8_t *mask;    // [B,Tm]
     const float *wg;        // [256][128][4]  rows 0..127: kernel rows of the attention input, 128..255: recurrent kernel
     const float *wtok;      // [7][128][4]    kernel row of token v + bias

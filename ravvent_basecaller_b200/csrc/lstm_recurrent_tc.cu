@@ -145,7 +145,9 @@ __device__ __forceinline__ void store_h8(unsigned char *hi_tile, unsigned char *
     *reinterpret_cast<uint4 *>(lo_tile + off) = lo_out;
 }
 
-template <int F, bool PRE>
+// NPASS = 3: fp32-parity split precision (h_lo.U_hi + h_hi.U_lo + h_hi.U_hi); NPASS = 1: reduced-precision mode,
+// a single h_hi.U_hi pass (fp16 operands, fp32 accumulate and cell state).
+template <int F, bool PRE, int NPASS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec_tc_kernel(Params p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -210,7 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 for (int j = 0; j < 2; ++j) {
                     const uint32_t d = tmem_base + (uint32_t)(j * 256);
 #pragma unroll
-                    for (int combo = 0; combo < 3; ++combo) {
+                    for (int combo = (NPASS == 3 ? 0 : 2); combo < 3; ++combo) {
                         const int pa = (combo == 0) ? 1 : 0;      // h_lo.U_hi, h_hi.U_lo, h_hi.U_hi
                         const int pb = (combo == 1) ? 1 : 0;
 #pragma unroll
@@ -222,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t ad = make_desc(abase + ks * 32);
                                 const uint64_t bd = make_desc(bb + ((j * 2 + pb) * 2 + kb) * TILE_BYTES + ks * 32);
-                                umma_f16_2sm(d, ad, bd, (combo | kb | ks) ? 1u : 0u);
+                                umma_f16_2sm(d, ad, bd, ((combo - (NPASS == 3 ? 0 : 2)) | kb | ks) ? 1u : 0u);
                             }
                         }
                     }
@@ -349,6 +351,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                     } else {
                         *reinterpret_cast<float4 *>(yrow + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
                         *reinterpret_cast<float4 *>(yrow + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);
+                        if (p.yv16 != nullptr)      // fp16 copy of the attention memory for the reduced-precision decoder
+                            *reinterpret_cast<uint4 *>(p.yv16 + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf + 8 * ch) = ph;
                     }
                     if (so != nullptr && s == T - 1) {
                         *reinterpret_cast<float4 *>(so + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
@@ -375,13 +379,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     }
 }
 
-template <int F, bool PRE>
+template <int F, bool PRE, int NPASS>
 static int launch(const Params &p, cudaStream_t stream) {
-    RVB_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<F, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    RVB_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<F, PRE, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const int clusters = (p.B + 2 * ROWS - 1) / (2 * ROWS) * 2;          // x 2 directions
     {
         ProfScope ps(KK_REC, stream);
-        lstm_rec_tc_kernel<F, PRE><<<dim3((unsigned)(clusters * 2)), THREADS, SMEM, stream>>>(p);
+        lstm_rec_tc_kernel<F, PRE, NPASS><<<dim3((unsigned)(clusters * 2)), THREADS, SMEM, stream>>>(p);
     }
     RVB_LAUNCH_CHECK();
     count_launch();
@@ -390,9 +394,10 @@ static int launch(const Params &p, cudaStream_t stream) {
 
 int run(int feat, const Params &p, cudaStream_t stream) {
     if (p.B <= 0 || p.T <= 0) return RVB_OK;
-    if (feat == 1) return launch<1, false>(p, stream);
-    if (feat == 5) return launch<5, false>(p, stream);
-    if (feat == 0) return launch<1, true>(p, stream);
+    const bool full = (p.precision == RVB_PREC_FP32);
+    if (feat == 1) return full ? launch<1, false, 3>(p, stream) : launch<1, false, 1>(p, stream);
+    if (feat == 5) return full ? launch<5, false, 3>(p, stream) : launch<5, false, 1>(p, stream);
+    if (feat == 0) return full ? launch<1, true, 3>(p, stream) : launch<1, true, 1>(p, stream);
     return fail(RVB_ERR_ARG, "lstm_rec_tc: unsupported feature count %d", feat);
 }
 
