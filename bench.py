@@ -275,7 +275,7 @@ def run_ours(args, rank, local_rank, world):
         h2d = C * (T_RAW + T_EV * 5) * 4
         d2h = C * S * 8 + 4
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only (contract)
             v, dt, thr = cpu_reference_rate(args.ref_chunks, args.beam)
             cpu = {"value": v, "unit": "bases/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": "%d joint chunks, beam%d, numpy/BLAS restatement of the TF path (oracle/model_ref.py), "
@@ -284,7 +284,7 @@ def run_ours(args, rank, local_rank, world):
             "metric": "read-equivalent bases/sec (joint model, beam%d)" % args.beam,
             "value": rate(ms1) * BASES_PER_CHUNK, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms1, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate", "data": "synthetic",
             "config": {"workload": "joint raw+event model (enc 2x BiLSTM-128, dec LSTM-128 + Luong), beam%d, "
                                    "S=33 decode steps, %d synthetic chunks per GPU" % (args.beam, C),
                        "chunks_per_gpu": C, "max_output_len": MAX_OUTPUT_LEN, "weights": "Keras-default init, seed 22",
@@ -305,7 +305,7 @@ def run_ours(args, rank, local_rank, world):
                                  "timed region; traffic = dram bytes of ONE launch on a 9472-chunk wave from the committed ncu "
                                  "capture (profiles/), scale by chunks/9472 to compare with a full step"},
             "kernels": kr, "step_ms": per_step_ms,
-            "event_path": event_path_bench(local_rank) if not args.no_event_path else None,
+            "event_path": event_path_bench(local_rank) if (not args.no_event_path and world == 1) else None,
         }
         if cpu:
             line["cpu_baseline"] = cpu
