@@ -28,6 +28,7 @@ SOURCES = {
     "lstm_recurrent_tc.cu": [],
     "proj_gemm.cu": [],
     "decoder.cu": [],
+    "decoder_wave.cu": [],
     "snippets.cu": ["-fmad=false"],
 }
 

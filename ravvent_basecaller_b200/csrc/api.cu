@@ -67,6 +67,10 @@ struct rvb_model {
     uint16_t *d_bimg[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_w0[2] = {nullptr, nullptr};
     float *d_wg1 = nullptr, *d_b1 = nullptr;
+    // wave-level beam decoder (decoder_wave.cu): tf32 hi/lo transposed weights + Keras-order token rows + workspace
+    float *dw_wg[2] = {nullptr, nullptr}, *dw_wm[2] = {nullptr, nullptr}, *dw_wa[2] = {nullptr, nullptr}, *dw_wtok = nullptr, *dw_ws = nullptr;
+    size_t dw_ws_rows = 0;
+    bool dec_wave = false;
     float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
     // workspace for one wave
     size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
@@ -140,6 +144,8 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     m->use_tc = gemm::tc_available() && !(g && strcmp(g, "simt") == 0);
     const char *r = getenv("RVB_REC");
     m->rec_tc = m->use_tc && !(r && strcmp(r, "ffma") == 0);
+    const char *dv = getenv("RVB_DECODER");
+    m->dec_wave = m->use_tc && decoder_depth == 1 && !(dv && strcmp(dv, "persistent") == 0);
     *out = m;
     return RVB_OK;
 }
@@ -294,6 +300,28 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
             RVB_CHECK(upload(m, &m->d_b1, b1));
         }
         RVB_CHECK(upload(m, &m->d_wtok, wtok));
+        if (m->dec_wave) {
+            // [att-input rows ; U] as a [256,512] weight in Keras gate order, W_mem^T [128,256], W_att [384,128]
+            std::vector<float> wcat((size_t)2 * UNITS * GATES), wtk((size_t)VOCAB * GATES), wmT((size_t)UNITS * ENC_OUT);
+            for (int k = 0; k < 2 * UNITS; ++k)
+                for (int n = 0; n < GATES; ++n)
+                    wcat[(size_t)k * GATES + n] = k < UNITS ? Wd->data[(size_t)(VOCAB + k) * GATES + n] : Ud->data[(size_t)(k - UNITS) * GATES + n];
+            for (int v = 0; v < VOCAB; ++v)
+                for (int n = 0; n < GATES; ++n) wtk[(size_t)v * GATES + n] = Wd->data[(size_t)v * GATES + n] + Bd->data[n];
+            for (int e = 0; e < ENC_OUT; ++e)
+                for (int d = 0; d < UNITS; ++d) wmT[(size_t)d * ENC_OUT + e] = Wm->data[(size_t)e * UNITS + d];
+            float *tmp = nullptr;
+            auto prep = [&](const std::vector<float> &w, int K, int N, float **pair) -> int {
+                RVB_CHECK(upload(m, &tmp, w));
+                RVB_CHECK(dmalloc(m, &pair[0], w.size()));
+                RVB_CHECK(dmalloc(m, &pair[1], w.size()));
+                return gemm::prepare_weights(tmp, pair[0], pair[1], K, N, nullptr);
+            };
+            RVB_CHECK(prep(wcat, 2 * UNITS, GATES, m->dw_wg));
+            RVB_CHECK(prep(wmT, UNITS, ENC_OUT, m->dw_wm));
+            RVB_CHECK(prep(Wa->data, UNITS + ENC_OUT, UNITS, m->dw_wa));
+            RVB_CHECK(upload(m, &m->dw_wtok, wtk));
+        }
         RVB_CHECK(upload(m, &m->d_wmem, Wm->data));
         std::vector<float> wmT((size_t)UNITS * ENC_OUT);
         for (int e = 0; e < ENC_OUT; ++e)
@@ -461,6 +489,25 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
+        if (beam && W >= 2 && m->dec_wave) {
+            const size_t rows = (size_t)m->wave * W;
+            if (rows > m->dw_ws_rows) {
+                dfree(m, m->dw_ws);
+                RVB_CHECK(dmalloc(m, &m->dw_ws, decw::workspace_floats((long long)rows)));
+                m->dw_ws_rows = rows;
+            }
+            decw::Params q{};
+            q.values = m->enc_out; q.mask = m->mask;
+            q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
+            q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
+            q.B = nb; q.Tm = Tm; q.W = W; q.S = S;
+            q.ids = d_ids + (size_t)b0 * S * W; q.scores = d_scores + (size_t)b0 * S * W;
+            q.step_ids = d_step_ids ? d_step_ids + (size_t)b0 * S * W : m->step_ids;
+            q.parent_ids = d_parent_ids ? d_parent_ids + (size_t)b0 * S * W : m->parent_ids;
+            q.steps = d_steps; q.ws = m->dw_ws; q.abort_flag = m->d_abort;
+            RVB_CHECK(decw::run(q, s));
+            continue;
+        }
         dec::Params p{};
         p.wmemT = m->d_wmemT; p.values = m->enc_out; p.values16 = m->enc_out16; p.mask = m->mask;
         p.wg = m->d_wg; p.wtok = m->d_wtok; p.wg1 = m->d_wg1; p.b1 = m->d_b1; p.depth = m->dec_depth; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;

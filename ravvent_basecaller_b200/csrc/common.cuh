@@ -30,12 +30,15 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 enum KernelKind { KK_EVENT = 0, KK_GEMM = 1, KK_REC = 2, KK_DECODER = 3, KK_OTHER = 4, KK_COUNT = 5 };
 void prof_record(int kind, cudaStream_t stream, bool begin);
 extern std::atomic<int> g_prof_on;
+inline int &prof_nest() { static thread_local int n = 0; return n; }
+// Only the outermost scope records: a multi-kernel stage (decoder_wave) owns the time of the GEMMs it launches.
 struct ProfScope {
     int kind; cudaStream_t stream; bool on;
-    ProfScope(int k, cudaStream_t s) : kind(k), stream(s), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
+    ProfScope(int k, cudaStream_t s) : kind(k), stream(s), on(g_prof_on.load(std::memory_order_relaxed) != 0 && prof_nest() == 0) {
+        ++prof_nest();
         if (on) prof_record(kind, stream, true);
     }
-    ~ProfScope() { if (on) prof_record(kind, stream, false); }
+    ~ProfScope() { --prof_nest(); if (on) prof_record(kind, stream, false); }
 };
 
 #define RVB_CUDA(expr)                                                                       \

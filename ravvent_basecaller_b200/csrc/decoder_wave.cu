@@ -1,0 +1,316 @@
+// K4 + K5, wave-level formulation for beam search with beam width >= 2.
+//
+// Same semantics as decoder.cu (tfa AttentionWrapper + LuongAttention + BeamSearchDecoder, reference
+// basecaller.py:296-315) but organised per decode step over ALL rows of a wave
+// (rows = snippets x beams, ~47 000 for a 9 472-snippet wave at beam 5), so that the dense parts run on the
+// tcgen05 projection kernel (K2, 3xTF32 = fp32 accuracy) instead of per-CTA FFMA loops that stall on L2 weight
+// streams.  Per step:
+//   gather_concat   X[r]   = [attention_prev[src(r)] | h_prev[src(r)]]      src(r) = row of the parent beam
+//   GEMM            Z      = X . [W_att_in ; U]                              (K 256, N 512)
+//   cell            h, c   = LSTM(Z + W_token[token] + b, c_prev[src])       h -> XA[:, 0:128]
+//   GEMM            Q'     = h . W_mem^T                                     (K 128, N 256; folded Luong query)
+//   attention       ctx    = softmax_mask(values . q') . values              one warp per snippet, beams share the stream
+//   GEMM            A      = [h | ctx] . W_attention_layer                   (K 384, N 128)
+//   fc_search       logits = A . fc + b; tfa _beam_search_step (warp top-k); per-step outputs, next token / parent
+// and after the last step gather_tree.  The beam reorder never moves state: consumers read rows through src(r).
+#include "kernels.cuh"
+
+namespace rvb {
+namespace decw {
+
+constexpr int WMAX = 9;
+constexpr float F32_MIN = -3.4028234663852886e38f;
+
+__device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) { return 2.0f * fsig(2.0f * x) - 1.0f; }
+
+// ---- X[r] = [att[src] | h[src]]  (h lives in XA[:, 0:128]) -------------------------------------------------
+__global__ void gather_concat_kernel(const float *__restrict__ att, const float *__restrict__ xa, const int32_t *__restrict__ parent,
+                                     float *__restrict__ X, long long rows, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 each
+    if (i >= rows * 64) return;
+    const long long r = i >> 6; const int q = (int)(i & 63);
+    const long long src = (r / W) * W + parent[r];
+    float4 v;
+    if (q < 32) v = __ldg(reinterpret_cast<const float4 *>(att + src * UNITS) + q);
+    else v = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + (q - 32));
+    reinterpret_cast<float4 *>(X + r * (2 * UNITS))[q] = v;
+}
+
+// ---- LSTM cell pointwise: Z [rows,512] Keras gate order, wtok [7,512] (kernel row of the token + bias) ---------
+__global__ void cell_kernel(const float *__restrict__ Z, const float *__restrict__ wtok, const int32_t *__restrict__ tok,
+                            const int32_t *__restrict__ parent, const float *__restrict__ c_in, float *__restrict__ c_out,
+                            float *__restrict__ xa, long long rows, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * UNITS) return;
+    const long long r = i >> 7; const int u = (int)(i & 127);
+    const long long src = (r / W) * W + parent[r];
+    const float *z = Z + r * GATES;
+    const float *wt = wtok + (size_t)tok[r] * GATES;
+    const float zi = z[u] + __ldg(wt + u), zf = z[UNITS + u] + __ldg(wt + UNITS + u);
+    const float zg = z[2 * UNITS + u] + __ldg(wt + 2 * UNITS + u), zo = z[3 * UNITS + u] + __ldg(wt + 3 * UNITS + u);
+    const float c = fsig(zf) * c_in[src * UNITS + u] + fsig(zi) * ftanh(zg);
+    c_out[i] = c;
+    xa[r * (3 * UNITS) + u] = fsig(zo) * ftanh(c);
+}
+
+// ---- masked softmax(values . q') . values, one warp per snippet (same scheme as decoder.cu phase 2b) ----------
+template <int WT>
+__global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ values, const uint8_t *__restrict__ mask,
+                                                        const float *__restrict__ Q, float *__restrict__ xa, int B, int Tm, int W) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const size_t bm = (size_t)b * Tm;
+    unsigned mbits = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int tt = 8 * lane + j;
+        if (tt < Tm && mask[bm + tt] != 0) mbits |= 1u << j;
+    }
+    float q[WT][8], acc[WT][8], mx[WT], den[WT];
+#pragma unroll
+    for (int w = 0; w < WT; ++w) {
+        mx[w] = -INFINITY; den[w] = 0.0f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { acc[w][e] = 0.0f; q[w][e] = 0.0f; }
+        if (w < W) {
+            const float *qr = Q + ((size_t)b * W + w) * ENC_OUT;
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(qr + 4 * lane));
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(qr + UNITS + 4 * lane));
+            q[w][0] = a.x; q[w][1] = a.y; q[w][2] = a.z; q[w][3] = a.w; q[w][4] = c.x; q[w][5] = c.y; q[w][6] = c.z; q[w][7] = c.w;
+        }
+    }
+    const float *vbase = values + bm * ENC_OUT + 4 * lane;
+    float4 cur[8], nxt[8];
+    unsigned vb_cur = __shfl_sync(0xffffffffu, mbits, 0) & 0xFu, vb_nxt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        cur[2 * j] = cur[2 * j + 1] = make_float4(0, 0, 0, 0);
+        if ((vb_cur >> j) & 1u) {
+            cur[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT));
+            cur[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT + UNITS));
+        }
+    }
+    for (int t0 = 0; t0 < Tm; t0 += 4) {
+        const int t1 = t0 + 4;
+        vb_nxt = 0;
+        if (t1 < Tm) vb_nxt = (__shfl_sync(0xffffffffu, mbits, t1 >> 3) >> (t1 & 7)) & 0xFu;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            nxt[2 * j] = nxt[2 * j + 1] = make_float4(0, 0, 0, 0);
+            if ((vb_nxt >> j) & 1u) {
+                nxt[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT));
+                nxt[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT + UNITS));
+            }
+        }
+        if (vb_cur != 0) {
+#pragma unroll
+            for (int w = 0; w < WT; ++w)
+                if (w < W) {
+                    float sj[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = cur[2 * j], c = cur[2 * j + 1];
+                        float d = a.x * q[w][0] + a.y * q[w][1] + a.z * q[w][2] + a.w * q[w][3] +
+                                  c.x * q[w][4] + c.y * q[w][5] + c.z * q[w][6] + c.w * q[w][7];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                        sj[j] = ((vb_cur >> j) & 1u) ? d : -INFINITY;
+                    }
+                    const float mn = fmaxf(fmaxf(mx[w], fmaxf(sj[0], sj[1])), fmaxf(sj[2], sj[3]));
+                    const float scale = __expf(mx[w] - mn);
+                    float pj[4], ps = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { pj[j] = __expf(sj[j] - mn); ps += pj[j]; }
+                    den[w] = den[w] * scale + ps;
+                    mx[w] = mn;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[w][e] *= scale;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = cur[2 * j], c = cur[2 * j + 1];
+                        acc[w][0] = fmaf(pj[j], a.x, acc[w][0]); acc[w][1] = fmaf(pj[j], a.y, acc[w][1]);
+                        acc[w][2] = fmaf(pj[j], a.z, acc[w][2]); acc[w][3] = fmaf(pj[j], a.w, acc[w][3]);
+                        acc[w][4] = fmaf(pj[j], c.x, acc[w][4]); acc[w][5] = fmaf(pj[j], c.y, acc[w][5]);
+                        acc[w][6] = fmaf(pj[j], c.z, acc[w][6]); acc[w][7] = fmaf(pj[j], c.w, acc[w][7]);
+                    }
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        vb_cur = vb_nxt;
+    }
+#pragma unroll
+    for (int w = 0; w < WT; ++w)
+        if (w < W) {
+            const float inv = (den[w] > 0.0f) ? 1.0f / den[w] : __int_as_float(0x7fc00000);   // all masked -> NaN like tfa
+            float *o = xa + ((size_t)b * W + w) * (3 * UNITS) + UNITS;
+            *reinterpret_cast<float4 *>(o + 4 * lane) = make_float4(acc[w][0] * inv, acc[w][1] * inv, acc[w][2] * inv, acc[w][3] * inv);
+            *reinterpret_cast<float4 *>(o + UNITS + 4 * lane) = make_float4(acc[w][4] * inv, acc[w][5] * inv, acc[w][6] * inv, acc[w][7] * inv);
+        }
+}
+
+// (value desc, index asc) warp arg-max; dead candidates carry idx = INT_MAX, val = -inf.
+__device__ __forceinline__ void warp_argmax(float &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+// ---- logits = A . fc + b ; tfa _beam_search_step ; one warp per snippet ------------------------------------------
+__global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict__ att, const float *__restrict__ wfc, const float *__restrict__ bfc,
+                                                        float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent,
+                                                        int32_t *first_done, float *scores, int32_t *step_ids, int32_t *parent_ids,
+                                                        int B, int W, int S, int t) {
+    __shared__ float a_s[4][WMAX * UNITS];
+    __shared__ float lg_s[4][WMAX * 8];
+    __shared__ float wfc_s[UNITS * VOCAB];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < UNITS * VOCAB; i += blockDim.x) wfc_s[i] = wfc[i];
+    const int b = blockIdx.x * 4 + wid;
+    const bool active = b < B;
+    if (active)
+        for (int i = lane; i < W * UNITS; i += 32) a_s[wid][i] = att[(size_t)b * W * UNITS + i];
+    __syncthreads();
+    if (!active) return;
+    for (int i = lane; i < W * VOCAB; i += 32) {
+        const int k = i / VOCAB, v = i % VOCAB;
+        float a = bfc[v];
+#pragma unroll 8
+        for (int d = 0; d < UNITS; ++d) a = fmaf(a_s[wid][k * UNITS + d], wfc_s[d * VOCAB + v], a);
+        lg_s[wid][k * 8 + v] = a;
+    }
+    __syncwarp();
+    const int n_cand = W * VOCAB;
+    const size_t r0 = (size_t)b * W;
+    float v0 = -INFINITY, v1 = -INFINITY; int i0 = 0x7fffffff, i1 = 0x7fffffff;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < n_cand) {
+            const int k = i / VOCAB, v = i % VOCAB;
+            float slp;
+            if (fin[r0 + k]) slp = (v == TOKEN_END) ? 0.0f : F32_MIN;
+            else {
+                const float *lg = lg_s[wid] + k * 8;
+                float m = lg[0];
+#pragma unroll
+                for (int q = 1; q < VOCAB; ++q) m = fmaxf(m, lg[q]);
+                float se = 0.0f;
+#pragma unroll
+                for (int q = 0; q < VOCAB; ++q) se += expf(lg[q] - m);
+                slp = (lg[v] - m) - logf(se);
+            }
+            const float tot = lp[r0 + k] + slp;
+            if (h == 0) { v0 = tot; i0 = i; } else { v1 = tot; i1 = i; }
+        }
+    }
+    float sel_v = 0.0f; int sel_i = 0;
+    for (int k = 0; k < W; ++k) {
+        float v; int i;
+        if (v0 > v1 || (v0 == v1 && i0 < i1)) { v = v0; i = i0; } else { v = v1; i = i1; }
+        warp_argmax(v, i);
+        if (lane == k) { sel_v = v; sel_i = i; }
+        if (i0 == i) { v0 = -INFINITY; i0 = 0x7fffffff; }
+        if (i1 == i) { v1 = -INFINITY; i1 = 0x7fffffff; }
+    }
+    int nfin = 1, nlen = 0, word = 0, par = 0;
+    if (lane < W) {
+        word = sel_i % VOCAB; par = sel_i / VOCAB;
+        const int pf = fin[r0 + par];
+        nfin = pf | (word == TOKEN_END);
+        nlen = len[r0 + par] + (pf ? 0 : 1);
+    }
+    __syncwarp();
+    if (lane < W) {
+        fin[r0 + lane] = nfin; len[r0 + lane] = nlen; lp[r0 + lane] = sel_v; tok[r0 + lane] = word; parent[r0 + lane] = par;
+        const size_t o = ((size_t)b * S + t) * W + lane;
+        scores[o] = sel_v; step_ids[o] = word; parent_ids[o] = par;
+    }
+    const unsigned allfin = __ballot_sync(0xffffffffu, lane >= W || nfin);
+    if (lane == 0 && allfin == 0xffffffffu && first_done[b] == S) first_done[b] = t;
+}
+
+__global__ void init_state_kernel(float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent, int32_t *first_done,
+                                  long long rows, int W, int S) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int k = (int)(r % W);
+    lp[r] = (k == 0) ? 0.0f : -INFINITY;
+    fin[r] = (k == 0) ? 0 : 1;
+    len[r] = 0; tok[r] = TOKEN_START; parent[r] = k;
+    if (k == 0) first_done[r / W] = S;
+}
+
+// gather_tree on [B,S,W] arrays + T = max over snippets of (first all-finished step + 1)
+__global__ void finalize_kernel(const int32_t *step_ids, const int32_t *parent_ids, const int32_t *len, const int32_t *first_done,
+                                int32_t *ids, int32_t *steps, int B, int W, int S) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B * W) return;
+    const int b = g / W, k = g % W;
+    int maxlen = 0;
+    for (int q = 0; q < W; ++q) maxlen = max(maxlen, len[b * W + q]);
+    const int L = min(S, maxlen);
+    const size_t o = (size_t)b * S * W;
+    for (int tt = L; tt < S; ++tt) ids[o + (size_t)tt * W + k] = TOKEN_END;
+    int par = k;
+    for (int level = L - 1; level >= 0; --level) {
+        ids[o + (size_t)level * W + k] = step_ids[o + (size_t)level * W + par];
+        par = parent_ids[o + (size_t)level * W + par];
+    }
+    bool done = false;
+    for (int tt = 0; tt < L; ++tt) {
+        int32_t *p = ids + o + (size_t)tt * W + k;
+        if (done) *p = TOKEN_END;
+        else if (*p == TOKEN_END) done = true;
+    }
+    if (k == 0) atomicMax(steps, min(first_done[b] + 1, S));
+}
+
+size_t workspace_floats(long long rows) {
+    // X 256 | Z 512 | XA 384 | Q 256 | ATT 128 | c x2 256 | lp 1  + ints: fin len tok parent 4 + first_done
+    return (size_t)rows * (256 + 512 + 384 + 256 + 128 + 256 + 1 + 4 + 1) + 64;
+}
+
+int run(const Params &p, cudaStream_t s) {
+    if (p.B <= 0 || p.S <= 0) return RVB_OK;
+    if (p.W < 2 || p.W > WMAX) return fail(RVB_ERR_ARG, "decoder_wave: beam width must be in [2,%d]", WMAX);
+    const long long rows = (long long)p.B * p.W;
+    float *X = p.ws, *Z = X + rows * 256, *XA = Z + rows * 512, *Q = XA + rows * 384, *ATT = Q + rows * 256;
+    float *c0 = ATT + rows * 128, *c1 = c0 + rows * 128, *lp = c1 + rows * 128;
+    int32_t *fin = reinterpret_cast<int32_t *>(lp + rows), *len = fin + rows, *tok = len + rows, *parent = tok + rows;
+    int32_t *first_done = parent + rows;
+    RVB_CUDA(cudaMemsetAsync(XA, 0, sizeof(float) * rows * 384, s));
+    RVB_CUDA(cudaMemsetAsync(ATT, 0, sizeof(float) * rows * 128, s));
+    RVB_CUDA(cudaMemsetAsync(c0, 0, sizeof(float) * rows * 128, s));
+    ProfScope ps(KK_DECODER, s);
+    init_state_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(lp, fin, len, tok, parent, first_done, rows, p.W, p.S);
+    RVB_LAUNCH_CHECK();
+    int nl = 1;
+    for (int t = 0; t < p.S; ++t) {
+        float *cin = (t & 1) ? c1 : c0, *cout = (t & 1) ? c0 : c1;
+        gather_concat_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, s>>>(ATT, XA, parent, X, rows, p.W);
+        RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
+        cell_kernel<<<(unsigned)((rows * UNITS + 255) / 256), 256, 0, s>>>(Z, p.wtok, tok, parent, cin, cout, XA, rows, p.W);
+        RVB_CHECK(gemm::run_tc(XA, p.wm_hiT, p.wm_loT, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, 3 * UNITS));
+        const unsigned ab = (unsigned)((p.B + 3) / 4);
+        if (p.W <= 5) attention_kernel<5><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W);
+        else attention_kernel<9><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W);
+        RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
+        fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
+                                            p.parent_ids, p.B, p.W, p.S, t);
+        RVB_LAUNCH_CHECK();
+        nl += 4;
+    }
+    finalize_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(p.step_ids, p.parent_ids, len, first_done, p.ids, p.steps, p.B, p.W, p.S);
+    RVB_LAUNCH_CHECK();
+    count_launch(nl + 1);
+    return RVB_OK;
+}
+
+}  // namespace decw
+}  // namespace rvb

@@ -47,8 +47,9 @@ namespace gemm {    // K2, proj_gemm.cu
 int run_simt(const float *A, const float *Bm, const float *bias, float *C, long long M, int N, int K, cudaStream_t s);
 // tcgen05 path: WhiT / WloT are the [N,K] tf32 hi / remainder parts made by prepare_weights
 int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaStream_t s);
+// lda: row pitch of A in elements (0 = K)
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
-           int precision, int *abort_flag, cudaStream_t s);
+           int precision, int *abort_flag, cudaStream_t s, long long lda = 0);
 bool tc_available();
 // fp16-plane path (A produced as hi/lo planes by K3): all operands fp16, 3 passes on the fp16 pipe
 int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t s);
@@ -81,5 +82,26 @@ struct Params {
 };
 int run(const Params &p, cudaStream_t stream);
 }  // namespace dec
+
+namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >= 2), decoder_wave.cu
+struct Params {
+    const float *values;        // [B,Tm,256]
+    const uint8_t *mask;        // [B,Tm]
+    const float *wg_hiT, *wg_loT;   // tf32 hi / lo of [att-input rows ; recurrent kernel], transposed [512,256], Keras gate order
+    const float *wm_hiT, *wm_loT;   // W_mem^T as a [K=128, N=256] weight, transposed [256,128]
+    const float *wa_hiT, *wa_loT;   // attention layer [384,128], transposed [128,384]
+    const float *wtok;          // [7][512] kernel row of token v + bias, Keras gate order
+    const float *wfc, *bfc;     // [128][7], [7]
+    int B, Tm, W, S;
+    int32_t *ids;               // predicted_ids [B,S,W]
+    float *scores;              // [B,S,W]
+    int32_t *step_ids, *parent_ids;   // [B,S,W]
+    int32_t *steps;             // atomicMax of T
+    float *ws;                  // workspace_floats(B*W) floats
+    int *abort_flag;
+};
+size_t workspace_floats(long long rows);
+int run(const Params &p, cudaStream_t stream);
+}  // namespace decw
 
 }  // namespace rvb

@@ -115,17 +115,17 @@ int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaSt
 }
 
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
-           int precision, int *abort_flag, cudaStream_t stream) {
+           int precision, int *abort_flag, cudaStream_t stream, long long lda) {
     if (M <= 0) return RVB_OK;
     if (N % 128 != 0 || K % tc::BK != 0) return fail(RVB_ERR_ARG, "gemm_tc: N %% 128 and K %% 32 must be 0 (N=%d K=%d)", N, K);
     const bool three = (precision == RVB_PREC_FP32);
     static const bool legacy = getenv("RVB_GEMM_NONPERSISTENT") != nullptr;      // A/B switch for profiling
-    if (N % 256 == 0 && !legacy) return three ? tc::launch_persistent<3, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
-                                              : tc::launch_persistent<1, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
-    if (N % 256 == 0) return three ? tc::launch<256, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
-                                   : tc::launch<256, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
-    return three ? tc::launch<128, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream)
-                 : tc::launch<128, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+    if (N % 256 == 0 && !legacy) return three ? tc::launch_persistent<3, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda)
+                                              : tc::launch_persistent<1, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda);
+    if (N % 256 == 0) return three ? tc::launch<256, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda)
+                                   : tc::launch<256, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda);
+    return three ? tc::launch<128, 3>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda)
+                 : tc::launch<128, 1>(A, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda);
 }
 
 // ---- fp16-plane path: x = hi + lo with hi = fp16(x), lo = fp16(x - hi) ------------------------------------

@@ -472,11 +472,12 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 row-major [rows, cols] tensor, box = BK columns x box_rows rows, 128-byte swizzle.
-inline int make_map(CUtensorMap *map, const void *base, long long rows, int cols, int box_rows, int box_cols = BK, bool f16 = false) {
+inline int make_map(CUtensorMap *map, const void *base, long long rows, int cols, int box_rows, int box_cols = BK, bool f16 = false,
+                    long long ld = 0) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * (f16 ? 2 : 4)};
+    cuuint64_t strides[1] = {(cuuint64_t)(ld > 0 ? ld : cols) * (f16 ? 2 : 4)};     // row pitch in bytes
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
@@ -488,10 +489,10 @@ inline int make_map(CUtensorMap *map, const void *base, long long rows, int cols
 
 template <int BN, int NPASS>
 int launch(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
-           int *abort_flag, cudaStream_t stream) {
+           int *abort_flag, cudaStream_t stream, long long lda = 0) {
     using cfg = Cfg<BN, NPASS>;
     CUtensorMap ma, mh, ml;
-    RVB_CHECK(make_map(&ma, A, M, K, BM));
+    RVB_CHECK(make_map(&ma, A, M, K, BM, BK, false, lda));
     RVB_CHECK(make_map(&mh, WhiT, N, K, BN));
     RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, BN));
     RVB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
@@ -508,12 +509,12 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
 // F16IN: A (and W) are given as fp16 hi / lo planes ([M,K] / [N,K] row-major), K-elements per stage = 64.
 template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
-                      long long M, int N, int K, int *abort_flag, cudaStream_t stream) {
+                      long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0) {
     using cfg = PCfg<NPASS, F16IN>;
     CUtensorMap ma, mal, mh, ml, mc;
     const int bk = cfg::K_PER_STAGE;
-    RVB_CHECK(make_map(&ma, A, M, K, BM, bk, F16IN));
-    RVB_CHECK(make_map(&mal, (NPASS == 3 && F16IN) ? Alo : A, M, K, BM, bk, F16IN));
+    RVB_CHECK(make_map(&ma, A, M, K, BM, bk, F16IN, lda));
+    RVB_CHECK(make_map(&mal, (NPASS == 3 && F16IN) ? Alo : A, M, K, BM, bk, F16IN, lda));
     RVB_CHECK(make_map(&mh, WhiT, N, K, PBN, bk, F16IN));
     RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, PBN, bk, F16IN));
     RVB_CHECK(make_map(&mc, C, M, N, BM, 32));
