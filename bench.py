@@ -266,7 +266,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- roofline of the dominant kernel (K3, persistent recurrent LSTM), timed live with CUDA events
     peak, peak_src = measured_peaks()
-    kr = kernel_rooflines(prof, args.steps, C, args.beam, peak)
+    kr = kernel_rooflines(prof, args.steps, C, args.beam, peak, args.precision)
     dom = max(kr, key=lambda k: kr[k]["ms"])
 
     line = None
@@ -297,7 +297,7 @@ def run_ours(args, rank, local_rank, world):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": kr[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kr[dom]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                         "frac": kr[dom]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dom) if args.precision == "fp32" else None, "peak_source": peak_src,
                          "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms1 * args.steps),
                          "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
                          "achieved_tflops": kr[dom]["tflops"],
@@ -314,7 +314,7 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def kernel_rooflines(prof, steps, chunks, beam, peak_hbm):
+def kernel_rooflines(prof, steps, chunks, beam, peak_hbm, precision="fp32"):
     """Per-kernel achieved rates from the library's CUDA-event timings over the timed region.
     Algorithmic work per chunk: see the constants at the top."""
     out = {}
@@ -328,12 +328,13 @@ def kernel_rooflines(prof, steps, chunks, beam, peak_hbm):
     # K2: projection GEMMs of encoder layer 1 (raw + event): 524288 FLOP and (256 in + 1024 out) * 4 B per timestep
     g_ms = prof["projection_gemm"]["ms"]
     g_flop = units * (T_RAW + T_EV) * 524288.0
-    g_bytes = units * (T_RAW + T_EV) * (256 + 1024) * 4.0
+    # reduced-precision mode: one fp16 plane in (fp32 mode reads hi + lo planes = the same bytes as fp32)
+    g_bytes = units * (T_RAW + T_EV) * (256 * (2.0 if precision == "bf16" else 4.0) + 1024 * 4.0)
     out["projection_gemm"] = {"ms": g_ms, "launches": prof["projection_gemm"]["launches"],
                               "gbs": g_bytes / (g_ms * 1e-3) / 1e9, "tflops": g_flop / (g_ms * 1e-3) / 1e12}
     # K4+K5: decoder: values streamed once per decode step (folded query), 33 steps
     d_ms = prof["decoder"]["ms"]
-    d_bytes = units * 33 * (T_RAW + T_EV) * 256 * 4.0
+    d_bytes = units * 33 * (T_RAW + T_EV) * 256 * (2.0 if precision == "bf16" else 4.0)   # fp16 memory copy in reduced mode
     d_flop = units * 33 * beam * 546048.0
     out["decoder"] = {"ms": d_ms, "launches": prof["decoder"]["launches"],
                       "gbs": d_bytes / (d_ms * 1e-3) / 1e9, "tflops": d_flop / (d_ms * 1e-3) / 1e12}
