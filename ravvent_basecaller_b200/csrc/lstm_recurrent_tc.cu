@@ -23,7 +23,14 @@
 namespace rvb {
 namespace rectc {
 
-constexpr int THREADS = 320;          // w0 spare, w1 TMEM alloc + MMA issue, w2..w9 epilogue
+#ifndef RVB_REC_EPI_WARPS
+#define RVB_REC_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = RVB_REC_EPI_WARPS;      // 8 or 16: TMEM lane quarter = warp % 4, column group = (warp - 2) / 4
+constexpr int CGROUPS = EPI_WARPS / 4;           // column groups per CTA (2 or 4)
+constexpr int UPT = UNITS / CGROUPS;             // units per epilogue thread (64 or 32)
+constexpr int CPT = UPT / 8;                     // 8-unit chunks per epilogue thread
+constexpr int THREADS = 64 + 32 * EPI_WARPS;     // w0 spare, w1 TMEM alloc + MMA issue, then the epilogue warps
 constexpr int ROWS = 128;             // batch rows per CTA
 constexpr int TILE_BYTES = 16384;     // [128 rows][64 fp16] K-major SW128 tile
 constexpr int A_BYTES = 4 * TILE_BYTES;     // (hi|lo) x (kb 0|1)
@@ -133,10 +140,12 @@ __device__ __forceinline__ void store_h8(unsigned char *hi_tile, unsigned char *
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __half h0 = __float2half_rn(h[2 * i]), h1 = __float2half_rn(h[2 * i + 1]);
-        const __half l0 = __float2half_rn(h[2 * i] - __half2float(h0)), l1 = __float2half_rn(h[2 * i + 1] - __half2float(h1));
-        hi[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        lo[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        // packed conversions (F2FP.PACK_AB) keep the split off the XU pipe, which the gate nonlinearities saturate
+        const __half2 hh = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(h[2 * i] - hf.x, h[2 * i + 1] - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t *>(&hh);
+        lo[i] = *reinterpret_cast<const uint32_t *>(&ll);
     }
     const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
     hi_out = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -182,7 +191,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
             for (int i = threadIdx.x; i < (F + 1) * GATES; i += THREADS) w0s[i] = __ldg(p.w0 + (size_t)dir * W0_FLOATS + i);
     }
     if (threadIdx.x == 0) {
-        mbar_init(h_ready, 16);          // 8 epilogue warps x 2 CTAs (only the leader CTA's copy is used)
+        mbar_init(h_ready, 2 * EPI_WARPS);   // epilogue warps x 2 CTAs (only the leader CTA's copy is used)
         mbar_init(&acc_full[0], 1);
         mbar_init(&acc_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -234,19 +243,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
         }
     } else if (warp >= 2) {
         // ================= epilogue warps: gates, cell update, next h ================================
-        const int q = warp & 3, hlf = (warp - 2) >> 2;
+        const int q = warp & 3, cg = (warp - 2) >> 2;
+        const int hlf = cg / (CGROUPS / 2);                 // 256-column half = K-block of the h this thread produces
+        const int ch0 = (cg % (CGROUPS / 2)) * CPT;         // first 8-unit chunk inside that K-block
         const int row = 32 * q + lane;
         const int b = b0 + row;
         const bool live = b < B;
-        float c[64];
+        float c[UPT];
         {
-            float h0[64];
+            float h0[UPT];
 #pragma unroll
-            for (int i = 0; i < 64; ++i) { c[i] = 0.0f; h0[i] = 0.0f; }
+            for (int i = 0; i < UPT; ++i) { c[i] = 0.0f; h0[i] = 0.0f; }
             if (p.state_in != nullptr && live) {
-                const float *si = p.state_in + (((size_t)b * 2 + dir) * 2) * UNITS + 64 * hlf;
+                const float *si = p.state_in + (((size_t)b * 2 + dir) * 2) * UNITS + UPT * cg;
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
+                for (int i = 0; i < UPT; i += 4) {
                     const float4 hv = *reinterpret_cast<const float4 *>(si + i);
                     const float4 cv = *reinterpret_cast<const float4 *>(si + UNITS + i);
                     h0[i] = hv.x; h0[i + 1] = hv.y; h0[i + 2] = hv.z; h0[i + 3] = hv.w;
@@ -254,12 +265,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 }
             }
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = 0; ch < CPT; ++ch) {
                 float h8[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) h8[u] = h0[8 * ch + u];
                 uint4 dh, dl;
-                store_h8(a_tiles + hlf * TILE_BYTES, a_tiles + (2 + hlf) * TILE_BYTES, row, ch, h8, dh, dl);
+                store_h8(a_tiles + hlf * TILE_BYTES, a_tiles + (2 + hlf) * TILE_BYTES, row, ch0 + ch, h8, dh, dl);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -270,7 +281,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
         float4 gnext[4];                       // pre-gates of the NEXT 16-column sub-chunk (software pipeline)
 #pragma unroll
         for (int i = 0; i < 4; ++i) gnext[i] = make_float4(0, 0, 0, 0);
-        float *so = (p.state_out != nullptr && live) ? p.state_out + (((size_t)b * 2 + dir) * 2) * UNITS + 64 * hlf : nullptr;
+        float *so = (p.state_out != nullptr && live) ? p.state_out + (((size_t)b * 2 + dir) * 2) * UNITS + UPT * cg : nullptr;
         for (int s = 0; s < T && ok; ++s) {
             const int t = dir ? T - 1 - s : s;
             float xin[F];
@@ -278,17 +289,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
 #pragma unroll
                 for (int f = 0; f < F; ++f) xin[f] = live ? __ldg(p.x + ((size_t)b * T + t) * F + f) : 0.0f;
             }
-            const float *grow = PRE ? p.G + (size_t)b * p.g_bs + (size_t)t * p.g_ts + dir * GATES + 256 * hlf : nullptr;
+            const float *grow = PRE ? p.G + (size_t)b * p.g_bs + (size_t)t * p.g_ts + dir * GATES + 4 * UPT * cg : nullptr;
             const float *grow_next = nullptr;
             if (PRE && s + 1 < T) {
                 const int tn = dir ? T - 2 - s : s + 1;
-                grow_next = p.G + (size_t)b * p.g_bs + (size_t)tn * p.g_ts + dir * GATES + 256 * hlf;
+                grow_next = p.G + (size_t)b * p.g_bs + (size_t)tn * p.g_ts + dir * GATES + 4 * UPT * cg;
             }
             if (PRE && s == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
             }
-            float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf : nullptr;
+            float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + UPT * cg : nullptr;
             // destination tiles of the next h: K-block 0 ping-pongs (home tiles on even steps, `alt` on odd ones)
             unsigned char *hi_dst = (hlf == 1) ? a_tiles + TILE_BYTES : ((OVL && ((s + 1) & 1)) ? alt : a_tiles);
             unsigned char *lo_dst = (hlf == 1) ? a_tiles + 3 * TILE_BYTES : ((OVL && ((s + 1) & 1)) ? alt + TILE_BYTES : a_tiles + 2 * TILE_BYTES);
@@ -296,25 +307,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
             if (!ok) break;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
+            for (int ch = 0; ch < CPT; ++ch) {
                 float h8[8];
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
-                    const int col = 32 * ch + 16 * sub;          // within this warp's 256-column half
+                    const int col = 32 * ch + 16 * sub;          // within this warp's 4*UPT-column group
                     uint32_t r[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(256 * hlf + col), r);
+                    tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * UPT * cg + col), r);
                     float z[16];
                     if (PRE) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { z[4 * i] = gnext[i].x; z[4 * i + 1] = gnext[i].y; z[4 * i + 2] = gnext[i].z; z[4 * i + 3] = gnext[i].w; }
                         // issue the loads of the following sub-chunk (or of the next step's first one) now
-                        const float *nsrc = (col + 16 < 256) ? grow + col + 16 : grow_next;
+                        const float *nsrc = (col + 16 < 4 * UPT) ? grow + col + 16 : grow_next;
                         if (live && nsrc != nullptr) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) gnext[i] = __ldg(reinterpret_cast<const float4 *>(nsrc + 4 * i));
                         }
                     } else {
-                        const float *wr = w0s + 256 * hlf + col;
+                        const float *wr = w0s + 4 * UPT * cg + col;
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
                             float4 a = *reinterpret_cast<const float4 *>(wr + F * GATES + i);          // bias row
@@ -342,17 +353,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                     }
                 }
                 uint4 ph, pl;
-                store_h8(hi_dst, lo_dst, row, ch, h8, ph, pl);
+                store_h8(hi_dst, lo_dst, row, ch0 + ch, h8, ph, pl);
                 if (live) {
                     if (p.y16_hi != nullptr) {          // intermediate layer: fp16 hi/lo planes for the next projection
-                        const size_t o = (size_t)b * p.y16_bs + (size_t)t * p.y16_ts + dir * UNITS + 64 * hlf + 8 * ch;
+                        const size_t o = (size_t)b * p.y16_bs + (size_t)t * p.y16_ts + dir * UNITS + UPT * cg + 8 * ch;
                         *reinterpret_cast<uint4 *>(p.y16_hi + o) = ph;
                         *reinterpret_cast<uint4 *>(p.y16_lo + o) = pl;
                     } else {
                         *reinterpret_cast<float4 *>(yrow + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
                         *reinterpret_cast<float4 *>(yrow + 8 * ch + 4) = make_float4(h8[4], h8[5], h8[6], h8[7]);
                         if (p.yv16 != nullptr)      // fp16 copy of the attention memory for the reduced-precision decoder
-                            *reinterpret_cast<uint4 *>(p.yv16 + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + 64 * hlf + 8 * ch) = ph;
+                            *reinterpret_cast<uint4 *>(p.yv16 + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + UPT * cg + 8 * ch) = ph;
                     }
                     if (so != nullptr && s == T - 1) {
                         *reinterpret_cast<float4 *>(so + 8 * ch) = make_float4(h8[0], h8[1], h8[2], h8[3]);
@@ -367,7 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
         }
         if (so != nullptr && ok) {
 #pragma unroll
-            for (int i = 0; i < 64; i += 4)
+            for (int i = 0; i < UPT; i += 4)
                 *reinterpret_cast<float4 *>(so + UNITS + i) = make_float4(c[i], c[i + 1], c[i + 2], c[i + 3]);
         }
     }
