@@ -163,6 +163,20 @@ int rvb_gather_tree(const int32_t *d_step_ids, const int32_t *d_parent_ids, cons
 int rvb_project(const float *d_a, const float *d_b, const float *d_bias, float *d_c,
                 int64_t m, int n, int k, int precision, void *stream);
 
+/* ---- snippet -> read stitching ---------------------------------------------
+ * rvb_beam_scores_to_probs: utils.calc_prob_logits_beam_search_scores (utils.py:123-128) on the
+ *   beam-0 scores of rvb_beam: probs[i,t] = exp(scores[i,t] - scores[i,t-1]), scores[i,-1] = 0.
+ * rvb_merge_reads: ravvent_performance_evaluator.py:66-74 -- tokens_to_nuc_sequences + SeqLogitsPair
+ *   per snippet, then Merger(scores_id).merge per read (merger.py:121-248, which calls Biopython
+ *   pairwise2.align.localms / localds on the 25-base overlaps).  Snippets of read r are rows
+ *   [read_offsets[r], read_offsets[r+1]) of d_ids / d_probs ([n_snippets, steps], device).  The merged
+ *   read r is written at d_seq_out / d_prob_out + read_offsets[r] * steps (buffers of n_snippets * steps
+ *   elements; bases as codes 0..3 = A C G T) with its length in d_len_out[r].  Synchronises the stream. */
+int rvb_beam_scores_to_probs(const float *d_scores, int64_t n_snippets, int steps, float *d_probs, void *stream);
+int rvb_merge_reads(const int32_t *d_ids, const float *d_probs, int64_t n_snippets, int steps,
+                    const int32_t *d_read_offsets, int n_reads, int scores_id,
+                    uint8_t *d_seq_out, float *d_prob_out, int32_t *d_len_out, void *stream);
+
 /* Introspection for bench.py: kernels launched by this library since load, and optional
  * per-kernel device timing (CUDA events on the launching stream).  rvb_profile(1) starts a
  * fresh recording, rvb_profile(0) stops; rvb_profile_read fills ms[5] / launches[5] in the order

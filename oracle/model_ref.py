@@ -349,6 +349,39 @@ def beam_scores_to_probs(beam_scores):
     return np.exp(s - prev)
 
 
+def masked_accuracy(y_true, y_pred, omit_vals):
+    """utils.masked_accuracy (utils.py:15-24): matches / positions whose target is not in omit_vals."""
+    total = count = 0
+    for t, p in zip(np.asarray(y_true).ravel().tolist(), np.asarray(y_pred).ravel().tolist()):
+        if t in [int(v) for v in omit_vals]:
+            continue
+        total += 1
+        count += int(t == p)
+    return count / total
+
+
+def val_step(w, enc_output, mask, target_tokens, decoder_depth=1):
+    """Basecaller._val_step (basecaller.py:267-279): greedy decode to the target length, zero-pad what
+    dynamic_decode did not produce, masked mean cross-entropy (padding target positions excluded,
+    basecaller.py:209-218) and masked accuracy (start / end targets excluded -- padding is NOT, as in the reference)."""
+    target_tokens = np.asarray(target_tokens)
+    L = target_tokens.shape[1]
+    ids, logits = greedy_search(w, enc_output, mask, L, decoder_depth=decoder_depth)
+    pad = L - 1 - ids.shape[1]
+    logits = np.pad(logits.astype(np.float64), [(0, 0), (0, pad), (0, 0)])
+    ids = np.pad(ids, [(0, 0), (0, pad)])
+    real = target_tokens[:, 1:]
+    num = den = 0.0
+    for b in range(real.shape[0]):
+        for t in range(real.shape[1]):
+            if real[b, t] == TOKEN_PAD:
+                continue
+            z = logits[b, t]
+            num += np.log(np.sum(np.exp(z - z.max()))) + z.max() - z[real[b, t]]
+            den += 1.0
+    return {"loss": num / den, "acc": masked_accuracy(real, ids, [TOKEN_START, TOKEN_END])}
+
+
 def called_bases(ids):
     """Bases (tokens 3..6) before the first end token, per row."""
     ids = np.asarray(ids)

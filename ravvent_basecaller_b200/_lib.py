@@ -50,6 +50,8 @@ _PROTOS = {
     "rvb_beam_step": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "rvb_gather_tree": (_i, [_p, _p, _p, _i, _i64, _i, _i, _p, _p]),
     "rvb_project": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p]),
+    "rvb_beam_scores_to_probs": (_i, [_p, _i64, _i, _p, _p]),
+    "rvb_merge_reads": (_i, [_p, _p, _i64, _i, _p, _i, _i, _p, _p, _p, _p]),
 }
 EXPORTS = tuple(_PROTOS)
 for _name, (_res, _args) in _PROTOS.items():

@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import tf_checkpoint as _tfckpt
 from . import weights as _weights
 
 
@@ -73,8 +74,9 @@ class Basecaller:
         return None
 
     def load_weights(self, source=None, *, seed=None):
-        """source: path to an .npz, or a dict name -> array (see weights.py); or seed=
-        for Keras-default random initialisation."""
+        """source: a Keras TF-format checkpoint prefix (as in ravvent_performance_evaluator.py:107; read by
+        tf_checkpoint.py without TensorFlow), a path to an .npz, or a dict name -> array (see weights.py);
+        or seed= for Keras-default random initialisation."""
         if source is None:
             w = _weights.random_weights(22 if seed is None else seed, self.enc_units, self.dec_units,
                                         self.encoder_depth, self.decoder_depth, self.vocab_size)
@@ -82,10 +84,13 @@ class Basecaller:
             w = source
         else:
             path = str(source)
-            if not path.endswith(".npz"):
-                raise NotImplementedError("only the .npz interchange is readable; Keras TF-format checkpoints "
-                                          "must be exported first (DESIGN.md, next rows)")
-            w = _weights.load_npz(path)
+            if path.endswith(".npz"):
+                w = _weights.load_npz(path)
+            elif _tfckpt.is_checkpoint_prefix(path):        # Keras TF-format prefix, as the reference passes it
+                w = _tfckpt.load_keras_checkpoint(path)
+            else:
+                raise FileNotFoundError(f"{path}: neither an .npz file nor a TF-format checkpoint prefix "
+                                        "(<prefix>.index / <prefix>.data-00000-of-00001)")
         for name, arr in w.items():
             if self.input_data_type == 'raw' and name.startswith('encoder_event'):
                 continue
@@ -210,6 +215,35 @@ class Basecaller:
         if host:
             return ids.cpu().numpy(), scores.cpu().numpy()
         return ids, scores
+
+    # -- validation (basecaller.py:209-218, 264-279) -----------------------------
+    def loss_function(self, real, pred):
+        """Mean sparse categorical cross-entropy from logits over the non-padding target positions."""
+        real = np.asarray(real).astype(np.int64)
+        pred = np.asarray(pred, dtype=np.float32)
+        m = pred.max(axis=-1, keepdims=True)
+        lse = (m + np.log(np.exp(pred - m).sum(axis=-1, keepdims=True, dtype=np.float32)))[..., 0]
+        loss = lse - np.take_along_axis(pred, real[..., None], axis=-1)[..., 0]
+        mask = (real != self.output_padding_token).astype(np.float32)
+        return np.float32((mask * loss).sum(dtype=np.float32) / mask.sum(dtype=np.float32))
+
+    def _val_step(self, data):
+        from .data_loader import masked_accuracy, unpack_data_to_input_target
+        input_data, target_tokens = unpack_data_to_input_target(data, self.input_data_type)
+        target_tokens = target_tokens.cpu().numpy() if isinstance(target_tokens, torch.Tensor) else np.asarray(target_tokens)
+        max_output_len = int(target_tokens.shape[1])
+        ids, logits = self.greedy_search_prediction(input_data, max_output_len=max_output_len)
+        if isinstance(ids, torch.Tensor):
+            ids, logits = ids.cpu().numpy(), logits.cpu().numpy()
+        pad = max_output_len - 1 - ids.shape[1]                 # dynamic_decode may have stopped early: zero-pad as the reference does
+        logits = np.pad(logits, [(0, 0), (0, pad), (0, 0)])
+        ids = np.pad(ids, [(0, 0), (0, pad)])
+        real = target_tokens[:, 1:]
+        return {'loss': self.loss_function(real, logits),
+                'acc': masked_accuracy(real, ids.astype(np.int64), [self.output_start_token, self.output_end_token])}
+
+    def test_step(self, inputs):
+        return self._val_step(inputs)
 
     def tokens_to_nuc_sequences(self, result_tokens):
         """ids -> text; strips ' ', '^', '$' and upper-cases (basecaller.py:289-294)."""

@@ -30,6 +30,7 @@ SOURCES = {
     "decoder.cu": [],
     "decoder_wave.cu": [],
     "snippets.cu": ["-fmad=false"],
+    "merger.cu": ["-fmad=false"],        # float64 alignment scores are compared exactly: no a*b+c contraction
 }
 
 

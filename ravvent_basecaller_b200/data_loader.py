@@ -47,6 +47,15 @@ def unpack_data_to_input_target(data, input_data_type):
     raise ValueError(input_data_type)
 
 
+def masked_accuracy(y_true, y_pred, omit_vals):
+    """Fraction of positions with y_true == y_pred among those whose y_true is not in omit_vals (utils.py:15-24)."""
+    y_true, y_pred = np.asarray(y_true), np.asarray(y_pred)
+    mask = np.ones(y_true.shape, dtype=np.int64)
+    for ov in omit_vals:
+        mask *= (y_true != ov).astype(np.int64)
+    return np.float64((mask * (y_true == y_pred)).sum()) / np.float64(mask.sum())
+
+
 def calc_prob_logits_beam_search_scores(beam_scores):
     """utils.calc_prob_logits_beam_search_scores (utils.py:123-128): per-base
     probability exp(score[t] - score[t-1]) from cumulative beam scores."""

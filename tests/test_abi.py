@@ -32,6 +32,8 @@ def test_no_cpu_fallback():
         rb.EventDetector(6, 9)
     with pytest.raises(rb.RavventError):
         rb.Basecaller(128, 128, 128, rb.nuc_tk, 'joint', 0.)
+    with pytest.raises(rb.RavventError):
+        rb.Merger()
 
 
 def test_product_does_not_import_oracle():
