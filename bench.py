@@ -43,7 +43,8 @@ REC_FLOP_PER_STEP_ROW = 131072            # recurrent FLOPs per timestep per dir
 REC_BYTES_L0 = 512 + 4                    # per step per row per direction, raw layer 0 (write h + read x)
 REC_BYTES_L1 = 2560                       # layer > 0: read 512 pre-gates + write 128 h (fp32)
 # dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/), 9472-chunk wave
-NCU_TRAFFIC = {"recurrent_lstm": 9.71e9, "decoder": 63.7e9, "projection_gemm": 9.65e9}
+# dram bytes of ONE launch on a 9 472-chunk wave (ncu --set full captures summarised under profiles/)
+NCU_TRAFFIC = {"recurrent_lstm": 9.71e9, "decoder": 63.7e9, "projection_gemm": 9.65e9, "attention": 1.949e9}
 
 
 def synth_chunks(rng, n):
@@ -266,7 +267,9 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- roofline of the dominant kernel (K3, persistent recurrent LSTM), timed live with CUDA events
     peak, peak_src = measured_peaks()
-    kr = kernel_rooflines(prof, args.steps, C, args.beam, peak, args.precision)
+    # memory rows the input mask admits (masked rows contribute nothing to the softmax and are not read)
+    valid_rows = float(((raw_d != 0).all(dim=-1).sum() + (ev_d != 0).all(dim=-1).sum()).item()) / C
+    kr = kernel_rooflines(prof, args.steps, C, args.beam, peak, args.precision, valid_rows)
     dom = max(kr, key=lambda k: kr[k]["ms"])
 
     line = None
@@ -301,9 +304,11 @@ def run_ours(args, rank, local_rank, world):
                          "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms1 * args.steps),
                          "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
                          "achieved_tflops": kr[dom]["tflops"],
-                         "note": "achieved = algorithmic bytes (DESIGN.md 4-5) / CUDA-event time of the kernel's launches in the "
-                                 "timed region; traffic = dram bytes of ONE launch on a 9472-chunk wave from the committed ncu "
-                                 "capture (profiles/), scale by chunks/9472 to compare with a full step"},
+                         "valid_memory_rows_per_chunk": valid_rows,
+                         "note": "achieved = algorithmic bytes (DESIGN.md 4.5-4.6: memory rows admitted by the mask x 1 KB per snippet "
+                                 "and decode step) / CUDA-event time of the kernel's launches in the timed region; peak = measured "
+                                 "copy bandwidth (a read-only stream can slightly exceed it); traffic = dram bytes of ONE launch on a "
+                                 "9472-chunk wave from the committed ncu capture (profiles/), launches here cover up to 9472 chunks each"},
             "kernels": kr, "step_ms": per_step_ms,
             "event_path": event_path_bench(local_rank) if (not args.no_event_path and world == 1) else None,
             "read_path": read_path_bench(local_rank, args.beam, args.precision) if (not args.no_event_path and world == 1) else None,
@@ -315,7 +320,7 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
-def kernel_rooflines(prof, steps, chunks, beam, peak_hbm, precision="fp32"):
+def kernel_rooflines(prof, steps, chunks, beam, peak_hbm, precision="fp32", valid_rows=float(T_RAW + T_EV)):
     """Per-kernel achieved rates from the library's CUDA-event timings over the timed region.
     Algorithmic work per chunk: see the constants at the top."""
     out = {}
@@ -337,8 +342,19 @@ def kernel_rooflines(prof, steps, chunks, beam, peak_hbm, precision="fp32"):
     d_ms = prof["decoder"]["ms"]
     d_bytes = units * 33 * (T_RAW + T_EV) * 256 * (2.0 if precision == "bf16" else 4.0)   # fp16 memory copy in reduced mode
     d_flop = units * 33 * beam * 546048.0
-    out["decoder"] = {"ms": d_ms, "launches": prof["decoder"]["launches"],
-                      "gbs": d_bytes / (d_ms * 1e-3) / 1e9, "tflops": d_flop / (d_ms * 1e-3) / 1e12}
+    a_ms = prof.get("attention", {"ms": 0.0})["ms"]
+    if a_ms > 0:
+        # wave-level decoder: the attention kernel (one launch per decode step and wave) is timed on its own; algorithmic
+        # bytes per launch = valid memory rows x 1 KB per snippet (all beams of a snippet share one pass) + the query / context rows
+        a_bytes = units * 33 * (valid_rows * 256 * 4.0 + beam * (256 + 256) * 4.0)
+        a_flop = units * 33 * beam * 768.0 * valid_rows
+        out["attention"] = {"ms": a_ms, "launches": prof["attention"]["launches"],
+                            "gbs": a_bytes / (a_ms * 1e-3) / 1e9, "tflops": a_flop / (a_ms * 1e-3) / 1e12}
+        d_bytes = units * 33 * beam * (256 + 512 + 512 + 384 + 256 + 384 + 128 + 128 + 128) * 4.0      # activations of the dense phases
+        d_flop -= a_flop
+    if d_ms > 0:
+        out["decoder"] = {"ms": d_ms, "launches": prof["decoder"]["launches"],
+                          "gbs": d_bytes / (d_ms * 1e-3) / 1e9, "tflops": d_flop / (d_ms * 1e-3) / 1e12}
     for k in out:
         out[k]["frac_hbm"] = out[k]["gbs"] / peak_hbm
     return out

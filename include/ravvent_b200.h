@@ -179,8 +179,9 @@ int rvb_merge_reads(const int32_t *d_ids, const float *d_probs, int64_t n_snippe
 
 /* Introspection for bench.py: kernels launched by this library since load, and optional
  * per-kernel device timing (CUDA events on the launching stream).  rvb_profile(1) starts a
- * fresh recording, rvb_profile(0) stops; rvb_profile_read fills ms[5] / launches[5] in the order
- * event scan, projection GEMM, recurrent LSTM, decoder, other (synchronises the device). */
+ * fresh recording, rvb_profile(0) stops; rvb_profile_read fills ms[6] / launches[6] (n >= 6) in the order
+ * event scan, projection GEMM, recurrent LSTM, decoder (dense phases + search), other, decoder attention
+ * (synchronises the device). */
 int64_t rvb_launch_count(void);
 int rvb_profile(int enable);
 int rvb_profile_read(double *ms, int64_t *launches, int n);

@@ -74,7 +74,7 @@ def launch_count() -> int:
     return int(lib.rvb_launch_count())
 
 
-KERNEL_KINDS = ("event_scan", "projection_gemm", "recurrent_lstm", "decoder", "other")
+KERNEL_KINDS = ("event_scan", "projection_gemm", "recurrent_lstm", "decoder", "other", "attention")
 
 
 def profile(enable: bool) -> None:
@@ -82,7 +82,7 @@ def profile(enable: bool) -> None:
 
 
 def profile_read() -> dict:
-    ms = (C.c_double * 5)()
-    n = (C.c_int64 * 5)()
-    check(lib.rvb_profile_read(ms, n, 5))
+    ms = (C.c_double * len(KERNEL_KINDS))()
+    n = (C.c_int64 * len(KERNEL_KINDS))()
+    check(lib.rvb_profile_read(ms, n, len(KERNEL_KINDS)))
     return {k: {"ms": ms[i], "launches": int(n[i])} for i, k in enumerate(KERNEL_KINDS)}

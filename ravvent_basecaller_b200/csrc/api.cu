@@ -489,7 +489,9 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
-        if (beam && W >= 2 && m->dec_wave) {
+        // Wave-level decoder for every beam width in parity mode; in reduced-precision mode width 1 stays on the persistent
+        // kernel, which streams the fp16 copy of the memory (half the bytes).  Greedy search keeps the persistent kernel.
+        if (beam && m->dec_wave && (W >= 2 || m->precision == RVB_PREC_FP32)) {
             const size_t rows = (size_t)m->wave * W;
             if (rows > m->dw_ws_rows) {
                 dfree(m, m->dw_ws);
@@ -605,7 +607,7 @@ extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, cons
 }
 
 // Per-kernel device time since rvb_profile(1): ms[k], launches[k] for k in KernelKind order
-// (event scan, projection GEMM, recurrent LSTM, decoder, other).  Synchronises the device.
+// (event scan, projection GEMM, recurrent LSTM, decoder, other, decoder attention).  Synchronises the device.
 extern "C" int rvb_profile(int enable) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto &e : g_prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }

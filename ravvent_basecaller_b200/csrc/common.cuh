@@ -27,7 +27,7 @@ extern std::atomic<long long> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- optional per-kernel timing (bench.py's roofline leg): CUDA events on the launching stream ----
-enum KernelKind { KK_EVENT = 0, KK_GEMM = 1, KK_REC = 2, KK_DECODER = 3, KK_OTHER = 4, KK_COUNT = 5 };
+enum KernelKind { KK_EVENT = 0, KK_GEMM = 1, KK_REC = 2, KK_DECODER = 3, KK_OTHER = 4, KK_ATTENTION = 5, KK_COUNT = 6 };
 void prof_record(int kind, cudaStream_t stream, bool begin);
 extern std::atomic<int> g_prof_on;
 inline int &prof_nest() { static thread_local int n = 0; return n; }
