@@ -279,12 +279,31 @@ struct PCfg {
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 1024 + 256;
 };
 
+// Multicast load: the box lands at the same CTA-relative offset in every CTA of `mask`, and each of them gets the
+// complete_tx on the mbarrier at the same CTA-relative offset.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_pair() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int NPASS, bool F16IN>
+// MC (fp16-plane encoder GEMM): CTAs are launched as clusters of two that walk the SAME column tile on adjacent row
+// tiles in lockstep; each loads half of the W stage and multicasts it to both, so a CTA pulls 64 KB instead of 96 KB per
+// stage out of L2 (the operand fill, not the MMA pipe, bounded the single-CTA form).  The MMAs stay cta_group::1; a
+// stage is released by both CTAs' commits (empty barriers count 2, commits multicast to the pair).
+template <int NPASS, bool F16IN, bool MC = false>
 __global__ void __launch_bounds__(PTHREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                           const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
@@ -301,11 +320,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = N / PBN;
-    const long long total = (long long)n_tiles * ((M + BM - 1) / BM);
+    const long long m_tiles = (M + BM - 1) / BM;
+    uint32_t rank = 0;
+    if (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    // work items: output tiles, or (MC) pairs of row-adjacent tiles of one column tile, one per CTA of the cluster
+    const long long total = (long long)n_tiles * (MC ? (m_tiles + 1) / 2 : m_tiles);
+    const long long w_first = MC ? (blockIdx.x >> 1) : blockIdx.x, w_step = MC ? (gridDim.x >> 1) : gridDim.x;
+    auto m_of = [&](long long w) -> long long { return MC ? 2 * (w / n_tiles) + rank : w / n_tiles; };
     const int num_kb = K / cfg::K_PER_STAGE;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], MC ? 2 : 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -317,6 +342,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (MC) cluster_sync_pair();                     // the peer's barriers exist before anything is multicast to them
 
     auto stage_a = [&](int s) { return smem + (size_t)s * cfg::STAGE_BYTES; };
     auto stage_bhi = [&](int s) { return stage_a(s) + ((NPASS == 3) ? 2 : 1) * cfg::A_BYTES; };
@@ -324,8 +350,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer =====
             long long g = 0; bool ok = true;
-            for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
-                const int n_tile = (int)(tile % n_tiles); const long long m_tile = tile / n_tiles;
+            for (long long tile = w_first; tile < total && ok; tile += w_step) {
+                const int n_tile = (int)(tile % n_tiles); const long long m_tile = m_of(tile);
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
                     if (round > 0 && !mbar_wait(&empty[s], (uint32_t)((round - 1) & 1), abort_flag)) { ok = false; break; }
@@ -333,8 +359,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const int kc = kb * cfg::K_PER_STAGE;
                     tma_load_2d(&map_a, &full[s], stage_a(s), kc, (int)(m_tile * BM));
                     if (NPASS == 3 && F16IN) tma_load_2d(&map_alo, &full[s], stage_a(s) + cfg::A_BYTES, kc, (int)(m_tile * BM));
-                    tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kc, n_tile * PBN);
-                    if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kc, n_tile * PBN);
+                    if (MC) {       // this CTA's half of the W rows (box = PBN / 2 rows), delivered to both CTAs
+                        const int half = (int)rank * (cfg::B_BYTES / 2), nrow = n_tile * PBN + (int)rank * (PBN / 2);
+                        tma_load_2d_mc(&map_bhi, &full[s], stage_bhi(s) + half, kc, nrow, (uint16_t)3);
+                        if (NPASS == 3) tma_load_2d_mc(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES + half, kc, nrow, (uint16_t)3);
+                    } else {
+                        tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kc, n_tile * PBN);
+                        if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kc, n_tile * PBN);
+                    }
                 }
             }
         }
@@ -342,7 +374,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         if (lane == 0) {                                   // ===== MMA issuer =====
             constexpr uint32_t idesc = F16IN ? make_idesc_f16(BM, PBN) : make_idesc_tf32(BM, PBN);
             long long g = 0, it = 0; bool ok = true;
-            for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++it) {
+            for (long long tile = w_first; tile < total && ok; tile += w_step, ++it) {
                 const int as = (int)(it & 1); const long long ar = it >> 1;
                 if (ar > 0 && !mbar_wait(&acc_empty[as], (uint32_t)((ar - 1) & 1), abort_flag)) { ok = false; break; }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -372,7 +404,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
                         }
                     }
-                    umma_commit(&empty[s]);
+                    if (MC) umma_commit_mc(&empty[s], (uint16_t)3); else umma_commit(&empty[s]);
                 }
                 if (ok) umma_commit(&acc_full[as]);
             }
@@ -381,7 +413,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         if (NPASS == 3 && !F16IN) {                        // ===== A split: hi in place, lo to the sibling buffer =====
             const int et = threadIdx.x - 128;
             long long g = 0; bool ok = true;
-            for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+            for (long long tile = w_first; tile < total && ok; tile += w_step) {
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
                     if (!mbar_wait(&full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
@@ -409,8 +441,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         const int row = q * 32 + lane;                     // row of the tile == TMEM lane
         const int et = threadIdx.x - 256;
         long long it = 0; int chunk_ctr = 0; bool ok = true;
-        for (long long tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++it) {
-            const int n_tile = (int)(tile % n_tiles); const long long m_tile = tile / n_tiles;
+        for (long long tile = w_first; tile < total && ok; tile += w_step, ++it) {
+            const int n_tile = (int)(tile % n_tiles); const long long m_tile = m_of(tile);
             const int as = (int)(it & 1); const long long ar = it >> 1;
             if (!mbar_wait(&acc_full[as], (uint32_t)(ar & 1), abort_flag)) { ok = false; break; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -447,6 +479,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (MC) cluster_sync_pair();                     // no multicast data / commit may still be on its way to a CTA that exits
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
@@ -511,21 +544,40 @@ template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
                       long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0) {
     using cfg = PCfg<NPASS, F16IN>;
-    CUtensorMap ma, mal, mh, ml, mc;
+    CUtensorMap ma, mal, mh, ml, mc_map;
     const int bk = cfg::K_PER_STAGE;
     RVB_CHECK(make_map(&ma, A, M, K, BM, bk, F16IN, lda));
     RVB_CHECK(make_map(&mal, (NPASS == 3 && F16IN) ? Alo : A, M, K, BM, bk, F16IN, lda));
-    RVB_CHECK(make_map(&mh, WhiT, N, K, PBN, bk, F16IN));
-    RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, PBN, bk, F16IN));
-    RVB_CHECK(make_map(&mc, C, M, N, BM, 32));
-    RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (long long)(N / PBN) * ((M + BM - 1) / BM);
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    { ProfScope ps(KK_GEMM, stream);
-      gemm_tc_persistent_kernel<NPASS, F16IN><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc, bias, M, N, K, abort_flag); }
+    const long long m_tiles = (M + BM - 1) / BM;
+    const long long tiles = (long long)(N / PBN) * m_tiles;
+    // cluster-of-two form with W multicast: the fp16-plane encoder GEMM when there is enough work for every SM pair
+    static const bool mc_off = getenv("RVB_GEMM_MC") && strcmp(getenv("RVB_GEMM_MC"), "0") == 0;
+    const bool mc = F16IN && NPASS == 3 && !mc_off && tiles >= 2LL * sms;
+    RVB_CHECK(make_map(&mh, WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
+    RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
+    RVB_CHECK(make_map(&mc_map, C, M, N, BM, 32));
+    if (mc) {
+        auto kern = gemm_tc_persistent_kernel<NPASS, F16IN, F16IN && NPASS == 3>;
+        RVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+        const long long pairs = (long long)(N / PBN) * ((m_tiles + 1) / 2);
+        const unsigned clusters = (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(2 * clusters); lc.blockDim = dim3(PTHREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        ProfScope ps(KK_GEMM, stream);
+        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag));
+    } else {
+        RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+        const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+        ProfScope ps(KK_GEMM, stream);
+        gemm_tc_persistent_kernel<NPASS, F16IN, false><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag);
+    }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;
