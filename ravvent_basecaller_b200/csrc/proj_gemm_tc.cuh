@@ -267,12 +267,14 @@ constexpr int PTHREADS = 384;
 constexpr int PBN = 256;
 constexpr int CSTAGE_BYTES = BM * 32 * 4;       // 128 rows x 32 fp32 columns
 
-template <int NPASS, bool F16IN = false>
+// PAIR: 0 = independent CTAs; 1 = cluster of two, W halves TMA-multicast to both; 2 = cluster of two driving one
+// cta_group::2 MMA (M 256 = both CTAs' row tiles, each CTA holds only its half of the W stage -> 3 stages fit).
+template <int NPASS, bool F16IN = false, int PAIR = 0>
 struct PCfg {
     static constexpr int A_BYTES = BM * BK * 4;
-    static constexpr int B_BYTES = PBN * BK * 4;
+    static constexpr int B_BYTES = (PAIR == 2 ? PBN / 2 : PBN) * BK * 4;
     static constexpr int STAGE_BYTES = (NPASS == 3) ? (2 * A_BYTES + 2 * B_BYTES) : (A_BYTES + B_BYTES);
-    static constexpr int STAGES = (NPASS == 3) ? 2 : 4;
+    static constexpr int STAGES = (NPASS == 3) ? (PAIR == 2 ? 3 : 2) : 4;
     // fp16-plane inputs: A_lo also arrives by TMA; a stage then covers 64 K-elements (128 bytes of fp16)
     static constexpr int TX_BYTES = ((NPASS == 3 && F16IN) ? 2 : 1) * A_BYTES + ((NPASS == 3) ? 2 : 1) * B_BYTES;
     static constexpr int K_PER_STAGE = F16IN ? 64 : 32;
@@ -290,6 +292,22 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {      // arrive on CTA `rank`'s copy of bar
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
 __device__ __forceinline__ void cluster_sync_pair() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -303,46 +321,56 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
 // tiles in lockstep; each loads half of the W stage and multicasts it to both, so a CTA pulls 64 KB instead of 96 KB per
 // stage out of L2 (the operand fill, not the MMA pipe, bounded the single-CTA form).  The MMAs stay cta_group::1; a
 // stage is released by both CTAs' commits (empty barriers count 2, commits multicast to the pair).
-template <int NPASS, bool F16IN, bool MC = false>
+template <int NPASS, bool F16IN, int PAIR = 0>
 __global__ void __launch_bounds__(PTHREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                           const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                           const __grid_constant__ CUtensorMap map_c,
                           const float *__restrict__ bias, long long M, int N, int K, int *abort_flag) {
-    using cfg = PCfg<NPASS, F16IN>;
+    using cfg = PCfg<NPASS, F16IN, PAIR>;
+    constexpr bool MC = PAIR == 1, SM2 = PAIR == 2;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char *cstage = smem + (size_t)cfg::STAGES * cfg::STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(cstage + 2 * CSTAGE_BYTES);
     uint64_t *full = bars, *ready = bars + cfg::STAGES, *empty = bars + 2 * cfg::STAGES;
     uint64_t *acc_full = bars + 3 * cfg::STAGES, *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *peer_full = acc_empty + 2;             // SM2, leader CTA: the peer's stage has landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(peer_full + cfg::STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = N / PBN;
     const long long m_tiles = (M + BM - 1) / BM;
     uint32_t rank = 0;
-    if (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     // work items: output tiles, or (MC) pairs of row-adjacent tiles of one column tile, one per CTA of the cluster
-    const long long total = (long long)n_tiles * (MC ? (m_tiles + 1) / 2 : m_tiles);
-    const long long w_first = MC ? (blockIdx.x >> 1) : blockIdx.x, w_step = MC ? (gridDim.x >> 1) : gridDim.x;
-    auto m_of = [&](long long w) -> long long { return MC ? 2 * (w / n_tiles) + rank : w / n_tiles; };
+    const long long total = (long long)n_tiles * (PAIR ? (m_tiles + 1) / 2 : m_tiles);
+    const long long w_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x, w_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
+    auto m_of = [&](long long w) -> long long { return PAIR ? 2 * (w / n_tiles) + rank : w / n_tiles; };
     const int num_kb = K / cfg::K_PER_STAGE;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], MC ? 2 : 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+        // SM2: the leader's acc_empty collects one arrival per epilogue warp of both CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], SM2 ? 16 : (F16IN ? 256 : 128)); }
+        for (int s = 0; s < cfg::STAGES; ++s) mbar_init(&peer_full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (SM2) { __syncthreads(); cluster_sync_pair(); }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (SM2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    if (MC) cluster_sync_pair();                     // the peer's barriers exist before anything is multicast to them
+    if (PAIR) cluster_sync_pair();                   // the peer's barriers / TMEM exist before anything is sent to them
 
     auto stage_a = [&](int s) { return smem + (size_t)s * cfg::STAGE_BYTES; };
     auto stage_bhi = [&](int s) { return stage_a(s) + ((NPASS == 3) ? 2 : 1) * cfg::A_BYTES; };
@@ -359,7 +387,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const int kc = kb * cfg::K_PER_STAGE;
                     tma_load_2d(&map_a, &full[s], stage_a(s), kc, (int)(m_tile * BM));
                     if (NPASS == 3 && F16IN) tma_load_2d(&map_alo, &full[s], stage_a(s) + cfg::A_BYTES, kc, (int)(m_tile * BM));
-                    if (MC) {       // this CTA's half of the W rows (box = PBN / 2 rows), delivered to both CTAs
+                    if (SM2) {      // this CTA's half of the W rows: the B operand of the pair's MMA is split across the CTAs
+                        const int nrow = n_tile * PBN + (int)rank * (PBN / 2);
+                        tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kc, nrow);
+                        if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kc, nrow);
+                    } else if (MC) {   // this CTA's half of the W rows (box = PBN / 2 rows), delivered to both CTAs
                         const int half = (int)rank * (cfg::B_BYTES / 2), nrow = n_tile * PBN + (int)rank * (PBN / 2);
                         tma_load_2d_mc(&map_bhi, &full[s], stage_bhi(s) + half, kc, nrow, (uint16_t)3);
                         if (NPASS == 3) tma_load_2d_mc(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES + half, kc, nrow, (uint16_t)3);
@@ -370,9 +402,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 }
             }
         }
+    } else if (warp == 1 && SM2 && rank == 1) {
+        if (lane == 0) {                                   // ===== peer CTA: tell the leader when a stage has landed here =====
+            long long g = 0; bool ok = true;
+            for (long long tile = w_first; tile < total && ok; tile += w_step)
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
+                    if (!mbar_wait(&full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
+                    mbar_arrive_cluster(&peer_full[s], 0);
+                }
+        }
     } else if (warp == 1) {
         if (lane == 0) {                                   // ===== MMA issuer =====
-            constexpr uint32_t idesc = F16IN ? make_idesc_f16(BM, PBN) : make_idesc_tf32(BM, PBN);
+            constexpr uint32_t idesc = F16IN ? make_idesc_f16(SM2 ? 2 * BM : BM, PBN) : make_idesc_tf32(BM, PBN);
             long long g = 0, it = 0; bool ok = true;
             for (long long tile = w_first; tile < total && ok; tile += w_step, ++it) {
                 const int as = (int)(it & 1); const long long ar = it >> 1;
@@ -382,13 +424,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
                     if (!mbar_wait((NPASS == 3 && !F16IN) ? &ready[s] : &full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
+                    if (SM2) {
+                        if (!mbar_wait(&peer_full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
+                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_bhi(s));
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {            // 4 x 32 bytes of K per 128-byte swizzle row
                         const uint32_t koff = ks * 32;
                         const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-                        if (F16IN) {
+                        if (SM2) {
+                            umma_f16_2sm(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
+                            umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
+                            umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+                        } else if (F16IN) {
                             if (NPASS == 3) {
                                 umma_f16(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
                                 umma_f16(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
@@ -404,13 +454,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             umma_tf32(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
                         }
                     }
-                    if (MC) umma_commit_mc(&empty[s], (uint16_t)3); else umma_commit(&empty[s]);
+                    if (SM2) umma_commit_2sm(&empty[s]); else if (MC) umma_commit_mc(&empty[s], (uint16_t)3); else umma_commit(&empty[s]);
                 }
-                if (ok) umma_commit(&acc_full[as]);
+                if (ok) { if (SM2) umma_commit_2sm(&acc_full[as]); else umma_commit(&acc_full[as]); }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        if (NPASS == 3 && !F16IN) {                        // ===== A split: hi in place, lo to the sibling buffer =====
+    } else if (warp >= 4 && warp < 8 && !F16IN) {
+        if (NPASS == 3) {                                  // ===== A split: hi in place, lo to the sibling buffer =====
             const int et = threadIdx.x - 128;
             long long g = 0; bool ok = true;
             for (long long tile = w_first; tile < total && ok; tile += w_step) {
@@ -435,11 +485,16 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers (+bias) -> swizzled smem staging -> TMA store =====
+        // fp32 inputs: one group (warps 8..11) with two staging buffers.  fp16-plane inputs need no split warps, so
+        // warps 4..7 form a second group: the groups take alternate 32-column chunks, one staging buffer and one
+        // named barrier each -- the epilogue, not the MMA pipe, bounded this kernel.
+        constexpr int NGRP = F16IN ? 2 : 1;
+        const int grp = (warp >= 8) ? 0 : 1;
         const int q = warp & 3;
         const int row = q * 32 + lane;                     // row of the tile == TMEM lane
-        const int et = threadIdx.x - 256;
+        const int et = threadIdx.x - (grp == 0 ? 256 : 128);
         long long it = 0; int chunk_ctr = 0; bool ok = true;
         for (long long tile = w_first; tile < total && ok; tile += w_step, ++it) {
             const int n_tile = (int)(tile % n_tiles); const long long m_tile = m_of(tile);
@@ -447,17 +502,21 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             if (!mbar_wait(&acc_full[as], (uint32_t)(ar & 1), abort_flag)) { ok = false; break; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c0 = 0; c0 < PBN; c0 += 32, ++chunk_ctr) {
+            for (int c0 = 32 * grp; c0 < PBN; c0 += 32 * NGRP, ++chunk_ctr) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * PBN + c0), r);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 == PBN) {                      // accumulator stage fully read: hand it back to the MMA warp
+                if (c0 + 32 * NGRP >= PBN) {               // this group's last read of the accumulator stage: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(&acc_empty[as]);
+                    if (SM2) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0); }
+                    else mbar_arrive(&acc_empty[as]);
                 }
-                unsigned char *cb = cstage + (chunk_ctr & 1) * CSTAGE_BYTES;
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store that last used cb has read it
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                unsigned char *cb = cstage + (NGRP == 2 ? grp : (chunk_ctr & 1)) * CSTAGE_BYTES;
+                if (et == 0) {                             // the store that last used cb has finished reading it
+                    if (NGRP == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                }
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
@@ -468,7 +527,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     *reinterpret_cast<float4 *>(cb + row * 128 + ((j ^ (row & 7)) << 4)) = v;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (et == 0) {
                     tma_store_2d(&map_c, cb, n_tile * PBN + c0, (int)(m_tile * BM));
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -479,9 +538,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (MC) cluster_sync_pair();                     // no multicast data / commit may still be on its way to a CTA that exits
+    if (PAIR) cluster_sync_pair();                   // nothing may still be on its way to a CTA that exits
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (SM2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -543,7 +603,9 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
 template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
                       long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0) {
-    using cfg = PCfg<NPASS, F16IN>;
+    constexpr int PAIRED = (F16IN && NPASS == 3) ? 2 : 0;         // cluster form used for the big encoder GEMM
+    using cfg = PCfg<NPASS, F16IN, 0>;
+    using cfgp = PCfg<NPASS, F16IN, PAIRED>;
     CUtensorMap ma, mal, mh, ml, mc_map;
     const int bk = cfg::K_PER_STAGE;
     RVB_CHECK(make_map(&ma, A, M, K, BM, bk, F16IN, lda));
@@ -553,19 +615,22 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long m_tiles = (M + BM - 1) / BM;
     const long long tiles = (long long)(N / PBN) * m_tiles;
-    // cluster-of-two form with W multicast: the fp16-plane encoder GEMM when there is enough work for every SM pair
-    static const bool mc_off = getenv("RVB_GEMM_MC") && strcmp(getenv("RVB_GEMM_MC"), "0") == 0;
-    const bool mc = F16IN && NPASS == 3 && !mc_off && tiles >= 2LL * sms;
+    // cluster-of-two forms of the fp16-plane encoder GEMM (RVB_GEMM_PAIR = 1: W halves multicast, 2: one 2-SM MMA per
+    // pair, 3 stages).  Both are correct and measured but not faster than independent CTAs, the default:
+    // the kernel is bound by its 4:1 write:read HBM stream, not by operand fill or pipeline depth.
+    static const int pair_env = getenv("RVB_GEMM_PAIR") ? atoi(getenv("RVB_GEMM_PAIR")) : 0;
+    const bool mc = PAIRED != 0 && pair_env != 0 && tiles >= 2LL * sms;
     RVB_CHECK(make_map(&mh, WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
     RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
     RVB_CHECK(make_map(&mc_map, C, M, N, BM, 32));
     if (mc) {
-        auto kern = gemm_tc_persistent_kernel<NPASS, F16IN, F16IN && NPASS == 3>;
-        RVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+        auto kern = (pair_env == 1) ? gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED ? 1 : 0> : gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED>;
+        const size_t smem_bytes = (pair_env == 1) ? cfg::SMEM : cfgp::SMEM;
+        RVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         const long long pairs = (long long)(N / PBN) * ((m_tiles + 1) / 2);
         const unsigned clusters = (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(2 * clusters); lc.blockDim = dim3(PTHREADS); lc.dynamicSmemBytes = cfg::SMEM; lc.stream = stream;
+        lc.gridDim = dim3(2 * clusters); lc.blockDim = dim3(PTHREADS); lc.dynamicSmemBytes = smem_bytes; lc.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -573,10 +638,10 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
         ProfScope ps(KK_GEMM, stream);
         RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag));
     } else {
-        RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
+        RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
         ProfScope ps(KK_GEMM, stream);
-        gemm_tc_persistent_kernel<NPASS, F16IN, false><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag);
+        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag);
     }
     RVB_LAUNCH_CHECK();
     count_launch();

@@ -251,3 +251,29 @@ def test_error_paths():
         bc._encode_input(np.zeros((2, 200, 3), np.float32))
     ids, sc = bc.beam_search_prediction(np.zeros((0, 200, 1), np.float32), 5, 10)
     assert ids.shape[0] == 0
+
+
+@pytest.mark.parametrize("pair", [1, 2])
+def test_projection_cluster_variants(pair):
+    """The cluster-of-two forms of the fp16-plane projection (RVB_GEMM_PAIR=1: W halves TMA-multicast, 2: one
+    cta_group::2 MMA per pair) are opt-in A/B variants; the mode is read once per process, hence the subprocess."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import numpy as np, torch
+        from ravvent_basecaller_b200 import _lib
+        rng = np.random.default_rng(5)
+        for M in (128 * 300 + 5, 128 * 296):
+            a = rng.normal(size=(M, 256)).astype(np.float32); b = (rng.normal(size=(256, 1024)) * 0.1).astype(np.float32)
+            bias = rng.normal(size=1024).astype(np.float32)
+            ta, tb, tbias = (torch.from_numpy(v).cuda() for v in (a, b, bias))
+            c = torch.full((M, 1024), float("nan"), dtype=torch.float32, device="cuda")
+            _lib.check(_lib.lib.rvb_project(ta.data_ptr(), tb.data_ptr(), tbias.data_ptr(), c.data_ptr(), M, 1024, 256, 2, None))
+            torch.cuda.synchronize()
+            err = np.abs(c.cpu().numpy() - (a.astype(np.float64) @ b.astype(np.float64) + bias)).max()
+            assert err < 5e-5, err
+        print("ok")
+    """)
+    env = dict(os.environ, RVB_GEMM_PAIR=str(pair))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
