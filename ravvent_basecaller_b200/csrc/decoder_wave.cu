@@ -54,6 +54,24 @@ __global__ void cell_kernel(const float *__restrict__ Z, const float *__restrict
     xa[r * (3 * UNITS) + u] = fsig(zo) * ftanh(c);
 }
 
+// ---- packed fp32 pairs: sm_100a executes two fp32 FMAs per issue slot (fma.rn.f32x2 -> FFMA2); nvcc does not pair them
+//      on its own, and the attention kernel below is issue bound on exactly these FMAs -------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// A memory row as this lane sees it: columns 4*lane..+3 and 128 + 4*lane..+3 as four packed pairs.
+struct Row8 { f32x2 p[4]; };
+__device__ __forceinline__ Row8 load_row8(const float *src) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src)), c = __ldg(reinterpret_cast<const uint4 *>(src + UNITS));
+    Row8 r;
+    r.p[0] = (f32x2)a.x | ((f32x2)a.y << 32); r.p[1] = (f32x2)a.z | ((f32x2)a.w << 32);
+    r.p[2] = (f32x2)c.x | ((f32x2)c.y << 32); r.p[3] = (f32x2)c.z | ((f32x2)c.w << 32);
+    return r;
+}
+
 // ---- masked softmax(values . q') . values, one warp per snippet (same scheme as decoder.cu phase 2b) ----------
 template <int WT>
 __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ values, const uint8_t *__restrict__ mask,
@@ -68,29 +86,26 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
         const int tt = 8 * lane + j;
         if (tt < Tm && mask[bm + tt] != 0) mbits |= 1u << j;
     }
-    float q[WT][8], acc[WT][8], mx[WT], den[WT];
+    f32x2 q[WT][4], acc[WT][4];
+    float mx[WT], den[WT];
 #pragma unroll
     for (int w = 0; w < WT; ++w) {
         mx[w] = -INFINITY; den[w] = 0.0f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { acc[w][e] = 0.0f; q[w][e] = 0.0f; }
+        for (int e = 0; e < 4; ++e) { acc[w][e] = 0ull; q[w][e] = 0ull; }
         if (w < W) {
-            const float *qr = Q + ((size_t)b * W + w) * ENC_OUT;
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(qr + 4 * lane));
-            const float4 c = __ldg(reinterpret_cast<const float4 *>(qr + UNITS + 4 * lane));
-            q[w][0] = a.x; q[w][1] = a.y; q[w][2] = a.z; q[w][3] = a.w; q[w][4] = c.x; q[w][5] = c.y; q[w][6] = c.z; q[w][7] = c.w;
+            const Row8 r = load_row8(Q + ((size_t)b * W + w) * ENC_OUT + 4 * lane);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) q[w][e] = r.p[e];
         }
     }
     const float *vbase = values + bm * ENC_OUT + 4 * lane;
-    float4 cur[8], nxt[8];
+    Row8 cur[4], nxt[4];
     unsigned vb_cur = __shfl_sync(0xffffffffu, mbits, 0) & 0xFu, vb_nxt = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        cur[2 * j] = cur[2 * j + 1] = make_float4(0, 0, 0, 0);
-        if ((vb_cur >> j) & 1u) {
-            cur[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT));
-            cur[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)j * ENC_OUT + UNITS));
-        }
+        cur[j].p[0] = cur[j].p[1] = cur[j].p[2] = cur[j].p[3] = 0ull;
+        if ((vb_cur >> j) & 1u) cur[j] = load_row8(vbase + (size_t)j * ENC_OUT);
     }
     for (int t0 = 0; t0 < Tm; t0 += 4) {
         const int t1 = t0 + 4;
@@ -98,11 +113,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
         if (t1 < Tm) vb_nxt = (__shfl_sync(0xffffffffu, mbits, t1 >> 3) >> (t1 & 7)) & 0xFu;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            nxt[2 * j] = nxt[2 * j + 1] = make_float4(0, 0, 0, 0);
-            if ((vb_nxt >> j) & 1u) {
-                nxt[2 * j] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT));
-                nxt[2 * j + 1] = __ldg(reinterpret_cast<const float4 *>(vbase + (size_t)(t1 + j) * ENC_OUT + UNITS));
-            }
+            nxt[j].p[0] = nxt[j].p[1] = nxt[j].p[2] = nxt[j].p[3] = 0ull;
+            if ((vb_nxt >> j) & 1u) nxt[j] = load_row8(vbase + (size_t)(t1 + j) * ENC_OUT);
         }
         if (vb_cur != 0) {
 #pragma unroll
@@ -111,9 +123,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
                     float sj[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 a = cur[2 * j], c = cur[2 * j + 1];
-                        float d = a.x * q[w][0] + a.y * q[w][1] + a.z * q[w][2] + a.w * q[w][3] +
-                                  c.x * q[w][4] + c.y * q[w][5] + c.z * q[w][6] + c.w * q[w][7];
+                        f32x2 d2 = mul2(cur[j].p[0], q[w][0]);
+                        d2 = fma2(cur[j].p[1], q[w][1], d2);
+                        d2 = fma2(cur[j].p[2], q[w][2], d2);
+                        d2 = fma2(cur[j].p[3], q[w][3], d2);
+                        float dl, dh;
+                        unpack2(d2, dl, dh);
+                        float d = dl + dh;
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
                         sj[j] = ((vb_cur >> j) & 1u) ? d : -INFINITY;
@@ -125,20 +141,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
                     for (int j = 0; j < 4; ++j) { pj[j] = __expf(sj[j] - mn); ps += pj[j]; }
                     den[w] = den[w] * scale + ps;
                     mx[w] = mn;
+                    const f32x2 sc2 = pack2(scale, scale);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[w][e] *= scale;
+                    for (int e = 0; e < 4; ++e) acc[w][e] = mul2(acc[w][e], sc2);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const float4 a = cur[2 * j], c = cur[2 * j + 1];
-                        acc[w][0] = fmaf(pj[j], a.x, acc[w][0]); acc[w][1] = fmaf(pj[j], a.y, acc[w][1]);
-                        acc[w][2] = fmaf(pj[j], a.z, acc[w][2]); acc[w][3] = fmaf(pj[j], a.w, acc[w][3]);
-                        acc[w][4] = fmaf(pj[j], c.x, acc[w][4]); acc[w][5] = fmaf(pj[j], c.y, acc[w][5]);
-                        acc[w][6] = fmaf(pj[j], c.z, acc[w][6]); acc[w][7] = fmaf(pj[j], c.w, acc[w][7]);
+                        const f32x2 p2 = pack2(pj[j], pj[j]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[w][e] = fma2(p2, cur[j].p[e], acc[w][e]);
                     }
                 }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
         vb_cur = vb_nxt;
     }
 #pragma unroll
@@ -146,8 +161,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
         if (w < W) {
             const float inv = (den[w] > 0.0f) ? 1.0f / den[w] : __int_as_float(0x7fc00000);   // all masked -> NaN like tfa
             float *o = xa + ((size_t)b * W + w) * (3 * UNITS) + UNITS;
-            *reinterpret_cast<float4 *>(o + 4 * lane) = make_float4(acc[w][0] * inv, acc[w][1] * inv, acc[w][2] * inv, acc[w][3] * inv);
-            *reinterpret_cast<float4 *>(o + UNITS + 4 * lane) = make_float4(acc[w][4] * inv, acc[w][5] * inv, acc[w][6] * inv, acc[w][7] * inv);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) unpack2(acc[w][e], v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<float4 *>(o + 4 * lane) = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
+            *reinterpret_cast<float4 *>(o + UNITS + 4 * lane) = make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
         }
 }
 

@@ -277,3 +277,21 @@ def test_projection_cluster_variants(pair):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("W,n", [(2, 5), (4, 1), (8, 6), (9, 7)])
+def test_beam_width_and_batch_edges(W, n):
+    """Every attention-kernel instantiation of the wave-level decoder (widths 1, <= 5, <= 9) and batches that do not
+    fill a CTA; interior masked rows (an exactly-zero sample inside the valid part of a chunk) are honoured."""
+    L = 12
+    raw, ev = mr.synth_chunks(np.random.default_rng(21 + W), n)
+    raw[0, 17, 0] = 0.0                                   # interior row masked out (utils.input_mask: any zero feature)
+    ev[n - 1, 3, :] = 0.0
+    ids, sc = make("joint").beam_search_prediction((raw, ev), W, L)
+    enc, mask = mr.encode_input(W22, (raw, ev), "joint")
+    assert not mask[0, 17] and not mask[n - 1, 200 + 3]
+    rid, rsc = mr.beam_search(W22, enc, mask, W, L)
+    assert ids.shape == rid.shape
+    same = np.array([np.array_equal(ids[b], rid[b]) for b in range(n)])
+    assert same.mean() >= 0.8, (same, ids, rid)
+    np.testing.assert_allclose(sc[same], rsc[same], rtol=RTOL, atol=1e-4)
