@@ -117,23 +117,33 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
             if ((vb_nxt >> j) & 1u) nxt[j] = load_row8(vbase + (size_t)(t1 + j) * ENC_OUT);
         }
         if (vb_cur != 0) {
+            // all WT x 4 dot products first, then ONE interleaved butterfly over them: the reductions of different beams
+            // are independent, and issuing them together hides the shuffle latency that a per-beam sequence exposes
+            float d[WT][4];
+#pragma unroll
+            for (int w = 0; w < WT; ++w)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    f32x2 d2 = mul2(cur[j].p[0], q[w][0]);
+                    d2 = fma2(cur[j].p[1], q[w][1], d2);
+                    d2 = fma2(cur[j].p[2], q[w][2], d2);
+                    d2 = fma2(cur[j].p[3], q[w][3], d2);
+                    float dl, dh;
+                    unpack2(d2, dl, dh);
+                    d[w][j] = dl + dh;
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int w = 0; w < WT; ++w)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[w][j] += __shfl_xor_sync(0xffffffffu, d[w][j], o);
 #pragma unroll
             for (int w = 0; w < WT; ++w)
                 if (w < W) {
                     float sj[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        f32x2 d2 = mul2(cur[j].p[0], q[w][0]);
-                        d2 = fma2(cur[j].p[1], q[w][1], d2);
-                        d2 = fma2(cur[j].p[2], q[w][2], d2);
-                        d2 = fma2(cur[j].p[3], q[w][3], d2);
-                        float dl, dh;
-                        unpack2(d2, dl, dh);
-                        float d = dl + dh;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                        sj[j] = ((vb_cur >> j) & 1u) ? d : -INFINITY;
-                    }
+                    for (int j = 0; j < 4; ++j) sj[j] = ((vb_cur >> j) & 1u) ? d[w][j] : -INFINITY;
                     const float mn = fmaxf(fmaxf(mx[w], fmaxf(sj[0], sj[1])), fmaxf(sj[2], sj[3]));
                     const float scale = __expf(mx[w] - mn);
                     float pj[4], ps = 0.0f;
