@@ -49,16 +49,42 @@ __device__ __forceinline__ float ftanh(float x) { return 2.0f * fsig(2.0f * x) -
 //   o*tanh(c'): o * (Cc - 2) / Cc                         Cc = 1 + e^{2 c'}
 // Arguments are clamped where the functions are saturated to < 1e-13 of their limit, which keeps every
 // product below 1e27 (no fp32 overflow).
+// The bare MUFU forms: every argument below is clamped first, so the range fix-ups that __expf / __fdividef wrap around
+// ex2.approx / rcp.approx (an FSETP, an FSEL and two or three FMULs each -- a third of this loop's issue slots) are dead code.
+__device__ __forceinline__ float ex2_raw(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_raw(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): the cell update is issue bound, and two units share every fp32 slot.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 ex2_2(f32x2 x) { float a, b; upk(x, a, b); return pk(ex2_raw(a), ex2_raw(b)); }
+__device__ __forceinline__ f32x2 rcp_2(f32x2 x) { float a, b; upk(x, a, b); return pk(rcp_raw(a), rcp_raw(b)); }
+__device__ __forceinline__ f32x2 max_2(f32x2 x, float m) { float a, b; upk(x, a, b); return pk(fmaxf(a, m), fmaxf(b, m)); }
+__device__ __forceinline__ f32x2 min_2(f32x2 x, float m) { float a, b; upk(x, a, b); return pk(fminf(a, m), fminf(b, m)); }
+
+// Two units at once.  One-sided clamps are enough: e^-z -> 0 and e^2z -> 0 on the far side are harmless, the clamped side
+// keeps A, F, O, G, Cc <= 1 + e^30 so that no product overflows (A*G <= 1e26) and rcp never sees inf.
+__device__ __forceinline__ void lstm_pointwise2(f32x2 zi, f32x2 zf, f32x2 zg, f32x2 zo, f32x2 c, f32x2 &cn, f32x2 &hn) {
+    constexpr float L2E = 1.4426950408889634f;
+    const f32x2 one = pk(1.0f, 1.0f), mtwo = pk(-2.0f, -2.0f), nl = pk(-L2E, -L2E), l2 = pk(2.0f * L2E, 2.0f * L2E);
+    const f32x2 A = add2(ex2_2(mul2(max_2(zi, -30.0f), nl)), one);
+    const f32x2 F = add2(ex2_2(mul2(max_2(zf, -30.0f), nl)), one);
+    const f32x2 O = add2(ex2_2(mul2(max_2(zo, -30.0f), nl)), one);
+    const f32x2 G = add2(ex2_2(mul2(min_2(zg, 15.0f), l2)), one);
+    const f32x2 ig = mul2(add2(G, mtwo), rcp_2(mul2(A, G)));
+    const f32x2 r = rcp_2(mul2(F, O));
+    cn = fma2(c, mul2(r, O), ig);
+    const f32x2 Cc = add2(ex2_2(mul2(min_2(cn, 15.0f), l2)), one);
+    hn = mul2(mul2(mul2(r, F), add2(Cc, mtwo)), rcp_2(Cc));
+}
 __device__ __forceinline__ void lstm_pointwise(float zi, float zf, float zg, float zo, float c, float &cn, float &hn) {
-    const float A = 1.0f + __expf(-fminf(fmaxf(zi, -30.0f), 30.0f));
-    const float F = 1.0f + __expf(-fminf(fmaxf(zf, -30.0f), 30.0f));
-    const float O = 1.0f + __expf(-fminf(fmaxf(zo, -30.0f), 30.0f));
-    const float G = 1.0f + __expf(2.0f * fminf(fmaxf(zg, -15.0f), 15.0f));
-    const float ig = (G - 2.0f) * __fdividef(1.0f, A * G);
-    const float r = __fdividef(1.0f, F * O);
-    cn = c * (r * O) + ig;
-    const float Cc = 1.0f + __expf(2.0f * fminf(fmaxf(cn, -15.0f), 15.0f));
-    hn = (r * F) * (Cc - 2.0f) * __fdividef(1.0f, Cc);
+    f32x2 c2, h2;
+    lstm_pointwise2(pk(zi, zi), pk(zf, zf), pk(zg, zg), pk(zo, zo), pk(c, c), c2, h2);
+    float t;
+    upk(c2, cn, t); upk(h2, hn, t);
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -278,9 +304,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
         if (lane == 0) mbar_arrive_remote(h_ready, 0);
 
         bool ok = true;
-        float4 gnext[4];                       // pre-gates of the NEXT 16-column sub-chunk (software pipeline)
+        float4 gnext[8];                       // pre-gates of the NEXT 32-column chunk (software pipeline)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gnext[i] = make_float4(0, 0, 0, 0);
+        for (int i = 0; i < 8; ++i) gnext[i] = make_float4(0, 0, 0, 0);
         float *so = (p.state_out != nullptr && live) ? p.state_out + (((size_t)b * 2 + dir) * 2) * UNITS + UPT * cg : nullptr;
         for (int s = 0; s < T && ok; ++s) {
             const int t = dir ? T - 1 - s : s;
@@ -297,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
             }
             if (PRE && s == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
+                for (int i = 0; i < 8; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
             }
             float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + UPT * cg : nullptr;
             // destination tiles of the next h: K-block 0 ping-pongs (home tiles on even steps, `alt` on odd ones)
@@ -308,49 +334,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int ch = 0; ch < CPT; ++ch) {
+                // one 32-column chunk = 8 units at a time: both 16-column TMEM loads are issued before the single wait, and the
+                // eight cell updates form one unrolled block, so eight independent EX2 -> RCP -> EX2 -> RCP chains are in flight
                 float h8[8];
+                const int col = 32 * ch;                      // within this warp's 4*UPT-column group
+                uint32_t r[32];
+                {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * UPT * cg + col), r0);
+                    tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * UPT * cg + col + 16), r1);
 #pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    const int col = 32 * ch + 16 * sub;          // within this warp's 4*UPT-column group
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * UPT * cg + col), r);
-                    float z[16];
-                    if (PRE) {
+                    for (int i = 0; i < 16; ++i) { r[i] = r0[i]; r[16 + i] = r1[i]; }
+                }
+                float z[32];
+                if (PRE) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { z[4 * i] = gnext[i].x; z[4 * i + 1] = gnext[i].y; z[4 * i + 2] = gnext[i].z; z[4 * i + 3] = gnext[i].w; }
-                        // issue the loads of the following sub-chunk (or of the next step's first one) now
-                        const float *nsrc = (col + 16 < 4 * UPT) ? grow + col + 16 : grow_next;
-                        if (live && nsrc != nullptr) {
+                    for (int i = 0; i < 8; ++i) { z[4 * i] = gnext[i].x; z[4 * i + 1] = gnext[i].y; z[4 * i + 2] = gnext[i].z; z[4 * i + 3] = gnext[i].w; }
+                    // issue the loads of the following chunk (or of the next step's first one) now
+                    const float *nsrc = (col + 32 < 4 * UPT) ? grow + col + 32 : grow_next;
+                    if (live && nsrc != nullptr) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) gnext[i] = __ldg(reinterpret_cast<const float4 *>(nsrc + 4 * i));
-                        }
-                    } else {
-                        const float *wr = w0s + 4 * UPT * cg + col;
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            float4 a = *reinterpret_cast<const float4 *>(wr + F * GATES + i);          // bias row
-#pragma unroll
-                            for (int f = 0; f < F; ++f) {
-                                const float4 w = *reinterpret_cast<const float4 *>(wr + f * GATES + i);
-                                a.x = fmaf(xin[f], w.x, a.x); a.y = fmaf(xin[f], w.y, a.y);
-                                a.z = fmaf(xin[f], w.z, a.z); a.w = fmaf(xin[f], w.w, a.w);
-                            }
-                            z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
-                        }
+                        for (int i = 0; i < 8; ++i) gnext[i] = __ldg(reinterpret_cast<const float4 *>(nsrc + 4 * i));
                     }
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                } else {
+                    const float *wr = w0s + 4 * UPT * cg + col;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float zi = z[4 * u + 0] + __uint_as_float(r[4 * u + 0]);
-                        const float zf = z[4 * u + 1] + __uint_as_float(r[4 * u + 1]);
-                        const float zg = z[4 * u + 2] + __uint_as_float(r[4 * u + 2]);
-                        const float zo = z[4 * u + 3] + __uint_as_float(r[4 * u + 3]);
-                        const int ci = 8 * ch + 4 * sub + u;
-                        float cn, hn;
-                        lstm_pointwise(zi, zf, zg, zo, c[ci], cn, hn);
-                        c[ci] = cn;
-                        h8[4 * sub + u] = hn;
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 a = *reinterpret_cast<const float4 *>(wr + F * GATES + i);          // bias row
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            const float4 w = *reinterpret_cast<const float4 *>(wr + f * GATES + i);
+                            a.x = fmaf(xin[f], w.x, a.x); a.y = fmaf(xin[f], w.y, a.y);
+                            a.z = fmaf(xin[f], w.z, a.z); a.w = fmaf(xin[f], w.w, a.w);
+                        }
+                        z[i] = a.x; z[i + 1] = a.y; z[i + 2] = a.z; z[i + 3] = a.w;
                     }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {                 // units u, u+1 as one packed pair
+                    const f32x2 zi = add2(pk(z[4 * u + 0], z[4 * u + 4]), pk(__uint_as_float(r[4 * u + 0]), __uint_as_float(r[4 * u + 4])));
+                    const f32x2 zf = add2(pk(z[4 * u + 1], z[4 * u + 5]), pk(__uint_as_float(r[4 * u + 1]), __uint_as_float(r[4 * u + 5])));
+                    const f32x2 zg = add2(pk(z[4 * u + 2], z[4 * u + 6]), pk(__uint_as_float(r[4 * u + 2]), __uint_as_float(r[4 * u + 6])));
+                    const f32x2 zo = add2(pk(z[4 * u + 3], z[4 * u + 7]), pk(__uint_as_float(r[4 * u + 3]), __uint_as_float(r[4 * u + 7])));
+                    const int ci = 8 * ch + u;
+                    f32x2 cn, hn;
+                    lstm_pointwise2(zi, zf, zg, zo, pk(c[ci], c[ci + 1]), cn, hn);
+                    upk(cn, c[ci], c[ci + 1]);
+                    upk(hn, h8[u], h8[u + 1]);
                 }
                 uint4 ph, pl;
                 store_h8(hi_dst, lo_dst, row, ch0 + ch, h8, ph, pl);
