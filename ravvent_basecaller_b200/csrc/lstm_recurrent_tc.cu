@@ -65,20 +65,24 @@ __device__ __forceinline__ f32x2 rcp_2(f32x2 x) { float a, b; upk(x, a, b); retu
 __device__ __forceinline__ f32x2 max_2(f32x2 x, float m) { float a, b; upk(x, a, b); return pk(fmaxf(a, m), fmaxf(b, m)); }
 __device__ __forceinline__ f32x2 min_2(f32x2 x, float m) { float a, b; upk(x, a, b); return pk(fminf(a, m), fminf(b, m)); }
 
-// Two units at once.  One-sided clamps are enough: e^-z -> 0 and e^2z -> 0 on the far side are harmless, the clamped side
-// keeps A, F, O, G, Cc <= 1 + e^30 so that no product overflows (A*G <= 1e26) and rcp never sees inf.
+// Two units at once.  One-sided clamps are enough: e^-z -> 0 and e^2z -> 0 on the far side are harmless; the clamped
+// side (sigmoid arguments >= -20, tanh arguments <= 10: both functions are within 5e-9 of their limits there, below
+// fp32 resolution of the gate values) keeps A, F, O, G <= 1 + e^20, so even A*G*F*O <= 5.5e34 is finite and ONE
+// reciprocal serves both quotients: 1/(A*G) = R*(F*O), 1/(F*O) = R*(A*G).  7 MUFU per unit (5 ex2 + 2 rcp).
 __device__ __forceinline__ void lstm_pointwise2(f32x2 zi, f32x2 zf, f32x2 zg, f32x2 zo, f32x2 c, f32x2 &cn, f32x2 &hn) {
     constexpr float L2E = 1.4426950408889634f;
     const f32x2 one = pk(1.0f, 1.0f), mtwo = pk(-2.0f, -2.0f), nl = pk(-L2E, -L2E), l2 = pk(2.0f * L2E, 2.0f * L2E);
-    const f32x2 A = add2(ex2_2(mul2(max_2(zi, -30.0f), nl)), one);
-    const f32x2 F = add2(ex2_2(mul2(max_2(zf, -30.0f), nl)), one);
-    const f32x2 O = add2(ex2_2(mul2(max_2(zo, -30.0f), nl)), one);
-    const f32x2 G = add2(ex2_2(mul2(min_2(zg, 15.0f), l2)), one);
-    const f32x2 ig = mul2(add2(G, mtwo), rcp_2(mul2(A, G)));
-    const f32x2 r = rcp_2(mul2(F, O));
-    cn = fma2(c, mul2(r, O), ig);
-    const f32x2 Cc = add2(ex2_2(mul2(min_2(cn, 15.0f), l2)), one);
-    hn = mul2(mul2(mul2(r, F), add2(Cc, mtwo)), rcp_2(Cc));
+    const f32x2 A = add2(ex2_2(mul2(max_2(zi, -20.0f), nl)), one);
+    const f32x2 F = add2(ex2_2(mul2(max_2(zf, -20.0f), nl)), one);
+    const f32x2 O = add2(ex2_2(mul2(max_2(zo, -20.0f), nl)), one);
+    const f32x2 G = add2(ex2_2(mul2(min_2(zg, 10.0f), l2)), one);
+    const f32x2 AG = mul2(A, G), FO = mul2(F, O);
+    const f32x2 R = rcp_2(mul2(AG, FO));
+    const f32x2 ig = mul2(add2(G, mtwo), mul2(R, FO));        // sigmoid(zi) * tanh(zg) = (G - 2) / (A G)
+    const f32x2 r = mul2(R, AG);                              // 1 / (F O)
+    cn = fma2(c, mul2(r, O), ig);                             // sigmoid(zf) = r O
+    const f32x2 Cc = add2(ex2_2(mul2(min_2(cn, 10.0f), l2)), one);
+    hn = mul2(mul2(mul2(r, F), add2(Cc, mtwo)), rcp_2(Cc));   // sigmoid(zo) tanh(c') = r F (Cc - 2) / Cc
 }
 __device__ __forceinline__ void lstm_pointwise(float zi, float zf, float zg, float zo, float c, float &cn, float &hn) {
     f32x2 c2, h2;
