@@ -345,7 +345,7 @@ static int project(rvb_model *m, int e, int l, const float *A, float *C, long lo
 }
 
 static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
-    const size_t wv = (size_t)m->wave;
+    const size_t wv = ((size_t)m->wave + 127) / 128 * 128;       // intermediates are padded to whole 128-row tiles
     const int Tm = t_raw + t_ev;
     if ((size_t)t_raw > m->ws_raw_t) {
         for (int i = 0; i < 2; ++i) { dfree(m, m->y_raw[i]); RVB_CHECK(dmalloc(m, &m->y_raw[i], wv * t_raw * ENC_OUT)); }
@@ -388,24 +388,26 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
         // tensor-core recurrence; intermediates are time-major (row = t*nb + b) so that a tile's rows of one
         // timestep are contiguous for both K2 and K3
         const bool last = (l == m->enc_depth - 1);
+        const long long nbp = ((long long)nb + 127) / 128 * 128;    // rows per timestep of the fp16 planes and of the blocked G
         rectc::Params p{};
-        p.x = x; p.G = G; p.g_bs = 2 * GATES; p.g_ts = (long long)nb * 2 * GATES;
+        p.x = x; p.G = G; p.g_bs = 2 * GATES; p.g_ts = nbp * 2 * GATES; p.g_blocked = 1; p.g_rows_per_t = nbp;
         p.bimg = m->d_bimg[e][l]; p.w0 = m->d_w0[e];
         p.state_in = l == 0 ? nullptr : m->st[e][(l - 1) & 1];
         p.state_out = m->st[e][l & 1];
         // intermediate layers hand their output to K2 as fp16 hi/lo planes (time-major, same bytes as fp32)
         uint16_t *pl_hi = reinterpret_cast<uint16_t *>(yb[l & 1]);
-        uint16_t *pl_lo = pl_hi + (size_t)nb * T * ENC_OUT;
+        uint16_t *pl_lo = pl_hi + (size_t)nbp * T * ENC_OUT;
         p.y = last ? out + (size_t)t_off * ENC_OUT : nullptr;
         p.y_bs = (long long)Tm * ENC_OUT; p.y_ts = ENC_OUT;
         p.y16_hi = last ? nullptr : pl_hi; p.y16_lo = last ? nullptr : pl_lo;
-        p.y16_bs = ENC_OUT; p.y16_ts = (long long)nb * ENC_OUT;
+        p.y16_bs = ENC_OUT; p.y16_ts = nbp * ENC_OUT;
         p.yv16 = (last && m->enc_out16 != nullptr && out == m->enc_out) ? m->enc_out16 + (size_t)t_off * ENC_OUT : nullptr;
         p.B = nb; p.T = T; p.abort_flag = m->d_abort; p.precision = m->precision;
         if (l > 0) {
             const uint16_t *a_hi = reinterpret_cast<const uint16_t *>(yb[(l - 1) & 1]);
-            RVB_CHECK(gemm::run_tc_f16(a_hi, a_hi + (size_t)nb * T * ENC_OUT, m->d_phi16[e][l], m->d_plo16[e][l], m->d_pb[e][l], G,
-                                       (long long)nb * T, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s));
+            // rows b >= nb of a timestep are padding: never written by K3, projected as they are, never read back
+            RVB_CHECK(gemm::run_tc_f16(a_hi, a_hi + (size_t)nbp * T * ENC_OUT, m->d_phi16[e][l], m->d_plo16[e][l], m->d_pb[e][l], G,
+                                       nbp * T, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s, true));
         }
         RVB_CHECK(rectc::run(l == 0 ? feat : 0, p, s));
     }

@@ -24,6 +24,8 @@ struct Params {
     const float *x;             // [B,T,F] batch-major (layer 0)
     const float *G;             // pre-gates (layer > 0): element (b,t,dir*512 + unit*4 + gate) at G[b*g_bs + t*g_ts + ...]
     long long g_bs, g_ts;
+    int g_blocked;              // 1: G is [row tile of 128][column quad][128 rows][4] with row = t * g_rows_per_t + b (coalesced by lane)
+    long long g_rows_per_t;     // padded batch (multiple of 128) of the blocked layout
     const uint16_t *bimg;       // [dir][rank] pre-swizzled fp16 hi/lo B-operand images (pack_b_image)
     const float *w0;            // [dir][6][512] layer-0 input rows + bias row, [unit][gate] column order
     const float *state_in;      // [B,2,2,128] or nullptr
@@ -55,7 +57,7 @@ bool tc_available();
 int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t s);
 int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cudaStream_t s);
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
-               int N, int K, int precision, int *abort_flag, cudaStream_t s);
+               int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false);
 }  // namespace gemm
 
 namespace dec {     // K4 + K5, decoder.cu

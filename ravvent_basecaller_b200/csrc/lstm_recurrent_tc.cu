@@ -319,15 +319,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
 #pragma unroll
                 for (int f = 0; f < F; ++f) xin[f] = live ? __ldg(p.x + ((size_t)b * T + t) * F + f) : 0.0f;
             }
-            const float *grow = PRE ? p.G + (size_t)b * p.g_bs + (size_t)t * p.g_ts + dir * GATES + 4 * UPT * cg : nullptr;
-            const float *grow_next = nullptr;
-            if (PRE && s + 1 < T) {
-                const int tn = dir ? T - 2 - s : s + 1;
-                grow_next = p.G + (size_t)b * p.g_bs + (size_t)tn * p.g_ts + dir * GATES + 4 * UPT * cg;
-            }
+            // pre-gates of (t, this row): float4 = one column quad; consecutive quads are gq apart.  Blocked layout (what
+            // K2 writes for the encoders): [row tile of 128][quad][row][4], so the 32 lanes of a warp read 512 contiguous bytes.
+            const long long gq = p.g_blocked ? ROWS : 1;
+            auto g_at = [&](int tt) -> const float4 * {
+                if (p.g_blocked) {
+                    const size_t rg = (size_t)tt * p.g_rows_per_t + b;
+                    return reinterpret_cast<const float4 *>(p.G) + ((rg >> 7) * (2 * GATES / 4) + dir * (GATES / 4) + UPT * cg) * ROWS + (rg & 127);
+                }
+                return reinterpret_cast<const float4 *>(p.G + (size_t)b * p.g_bs + (size_t)tt * p.g_ts + dir * GATES + 4 * UPT * cg);
+            };
+            const float4 *grow = PRE ? g_at(t) : nullptr;
+            const float4 *grow_next = nullptr;
+            if (PRE && s + 1 < T) grow_next = g_at(dir ? T - 2 - s : s + 1);
             if (PRE && s == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) gnext[i] = live ? __ldg(reinterpret_cast<const float4 *>(grow + 4 * i)) : make_float4(0, 0, 0, 0);
+                for (int i = 0; i < 8; ++i) gnext[i] = live ? __ldg(grow + i * gq) : make_float4(0, 0, 0, 0);
             }
             float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS + UPT * cg : nullptr;
             // destination tiles of the next h: K-block 0 ping-pongs (home tiles on even steps, `alt` on odd ones)
@@ -355,10 +362,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { z[4 * i] = gnext[i].x; z[4 * i + 1] = gnext[i].y; z[4 * i + 2] = gnext[i].z; z[4 * i + 3] = gnext[i].w; }
                     // issue the loads of the following chunk (or of the next step's first one) now
-                    const float *nsrc = (col + 32 < 4 * UPT) ? grow + col + 32 : grow_next;
+                    const float4 *nsrc = (col + 32 < 4 * UPT) ? grow + ((col + 32) >> 2) * gq : grow_next;
                     if (live && nsrc != nullptr) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) gnext[i] = __ldg(reinterpret_cast<const float4 *>(nsrc + 4 * i));
+                        for (int i = 0; i < 8; ++i) gnext[i] = __ldg(nsrc + i * gq);
                     }
                 } else {
                     const float *wr = w0s + 4 * UPT * cg + col;

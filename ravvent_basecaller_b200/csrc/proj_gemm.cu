@@ -161,12 +161,15 @@ int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cuda
     count_launch();
     return RVB_OK;
 }
+// blocked_out: C is written as [M / 128][N / 4][128 rows][4] (M % 128 == 0) with plain coalesced stores -- the layout
+// the recurrent kernel reads lane-contiguously -- instead of row-major through the staged TMA store.
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
-               int N, int K, int precision, int *abort_flag, cudaStream_t stream) {
+               int N, int K, int precision, int *abort_flag, cudaStream_t stream, bool blocked_out) {
     if (M <= 0) return RVB_OK;
     if (N % 256 != 0 || K % 64 != 0) return fail(RVB_ERR_ARG, "gemm_tc_f16: N %% 256 and K %% 64 must be 0 (N=%d K=%d)", N, K);
-    if (precision == RVB_PREC_FP32) return tc::launch_persistent<3, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
-    return tc::launch_persistent<1, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream);
+    if (blocked_out && M % 128 != 0) return fail(RVB_ERR_ARG, "gemm_tc_f16: blocked output needs M %% 128 == 0 (M=%lld)", M);
+    if (precision == RVB_PREC_FP32) return tc::launch_persistent<3, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, 0, blocked_out);
+    return tc::launch_persistent<1, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, 0, blocked_out);
 }
 
 }  // namespace gemm

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(PTHREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                           const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                           const __grid_constant__ CUtensorMap map_c,
-                          const float *__restrict__ bias, long long M, int N, int K, int *abort_flag) {
+                          const float *__restrict__ bias, long long M, int N, int K, int *abort_flag, float *__restrict__ c_blocked) {
     using cfg = PCfg<NPASS, F16IN, PAIR>;
     constexpr bool MC = PAIR == 1, SM2 = PAIR == 2;
     extern __shared__ unsigned char smem_dyn[];
@@ -511,6 +511,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     if (SM2) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0); }
                     else mbar_arrive(&acc_empty[as]);
                 }
+                if (c_blocked != nullptr) {                // blocked layout: lane = row, 16 bytes per lane, 512 contiguous bytes per warp store
+                    float4 *dst = reinterpret_cast<float4 *>(c_blocked) + ((size_t)m_tile * (N >> 2) + ((n_tile * PBN + c0) >> 2)) * BM + row;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        if (bias != nullptr) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)n_tile * PBN + c0 + 4 * j));
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        dst[(size_t)j * BM] = v;
+                    }
+                    continue;
+                }
                 unsigned char *cb = cstage + (NGRP == 2 ? grp : (chunk_ctr & 1)) * CSTAGE_BYTES;
                 if (et == 0) {                             // the store that last used cb has finished reading it
                     if (NGRP == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -602,7 +615,8 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
 // F16IN: A (and W) are given as fp16 hi / lo planes ([M,K] / [N,K] row-major), K-elements per stage = 64.
 template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
-                      long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0) {
+                      long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0, bool blocked_out = false) {
+    float *c_blocked = blocked_out ? C : nullptr;
     constexpr int PAIRED = (F16IN && NPASS == 3) ? 2 : 0;         // cluster form used for the big encoder GEMM
     using cfg = PCfg<NPASS, F16IN, 0>;
     using cfgp = PCfg<NPASS, F16IN, PAIRED>;
@@ -636,12 +650,12 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
         ProfScope ps(KK_GEMM, stream);
-        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag));
+        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked));
     } else {
         RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
         ProfScope ps(KK_GEMM, stream);
-        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag);
+        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked);
     }
     RVB_LAUNCH_CHECK();
     count_launch();
