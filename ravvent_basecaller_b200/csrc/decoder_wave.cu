@@ -1,17 +1,17 @@
-// K4 + K5, wave-level formulation for beam search with beam width >= 2.
+// K4 + K5, wave-level formulation for beam search (every beam width; greedy search keeps decoder.cu).
 //
 // Same semantics as decoder.cu (tfa AttentionWrapper + LuongAttention + BeamSearchDecoder, reference
 // basecaller.py:296-315) but organised per decode step over ALL rows of a wave
 // (rows = snippets x beams, ~47 000 for a 9 472-snippet wave at beam 5), so that the dense parts run on the
 // tcgen05 projection kernel (K2, 3xTF32 = fp32 accuracy) instead of per-CTA FFMA loops that stall on L2 weight
 // streams.  Per step:
-//   gather_concat   X[r]   = [attention_prev[src(r)] | h_prev[src(r)]]      src(r) = row of the parent beam
+//   (X[r] = [attention_prev[src(r)] | h_prev[src(r)]], src(r) = row of the parent beam, is written by the previous step's fc_search)
 //   GEMM            Z      = X . [W_att_in ; U]                              (K 256, N 512)
 //   cell            h, c   = LSTM(Z + W_token[token] + b, c_prev[src])       h -> XA[:, 0:128]
 //   GEMM            Q'     = h . W_mem^T                                     (K 128, N 256; folded Luong query)
 //   attention       ctx    = softmax_mask(values . q') . values              one warp per snippet, beams share the stream
 //   GEMM            A      = [h | ctx] . W_attention_layer                   (K 384, N 128)
-//   fc_search       logits = A . fc + b; tfa _beam_search_step (warp top-k); per-step outputs, next token / parent
+//   fc_search       logits = A . fc + b; tfa _beam_search_step (warp top-k); per-step outputs, next token / parent, next X
 // and after the last step gather_tree.  The beam reorder never moves state: consumers read rows through src(r).
 #include "kernels.cuh"
 
@@ -23,19 +23,6 @@ constexpr float F32_MIN = -3.4028234663852886e38f;
 
 __device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ftanh(float x) { return 2.0f * fsig(2.0f * x) - 1.0f; }
-
-// ---- X[r] = [att[src] | h[src]]  (h lives in XA[:, 0:128]) -------------------------------------------------
-__global__ void gather_concat_kernel(const float *__restrict__ att, const float *__restrict__ xa, const int32_t *__restrict__ parent,
-                                     float *__restrict__ X, long long rows, int W) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 each
-    if (i >= rows * 64) return;
-    const long long r = i >> 6; const int q = (int)(i & 63);
-    const long long src = (r / W) * W + parent[r];
-    float4 v;
-    if (q < 32) v = __ldg(reinterpret_cast<const float4 *>(att + src * UNITS) + q);
-    else v = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + (q - 32));
-    reinterpret_cast<float4 *>(X + r * (2 * UNITS))[q] = v;
-}
 
 // ---- LSTM cell pointwise: Z [rows,512] Keras gate order, wtok [7,512] (kernel row of the token + bias) ---------
 __global__ void cell_kernel(const float *__restrict__ Z, const float *__restrict__ wtok, const int32_t *__restrict__ tok,
@@ -193,7 +180,7 @@ __device__ __forceinline__ void warp_argmax(float &v, int &i) {
 __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict__ att, const float *__restrict__ wfc, const float *__restrict__ bfc,
                                                         float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent,
                                                         int32_t *first_done, float *scores, int32_t *step_ids, int32_t *parent_ids,
-                                                        int B, int W, int S, int t) {
+                                                        int B, int W, int S, int t, const float *__restrict__ xa, float *__restrict__ X) {
     __shared__ float a_s[4][WMAX * UNITS];
     __shared__ float lg_s[4][WMAX * 8];
     __shared__ float wfc_s[UNITS * VOCAB];
@@ -261,6 +248,13 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     }
     const unsigned allfin = __ballot_sync(0xffffffffu, lane >= W || nfin);
     if (lane == 0 && allfin == 0xffffffffu && first_done[b] == S) first_done[b] = t;
+    // input of the next step's cell GEMM, gathered through the parents chosen just now: X[r] = [attention[src] | h[src]]
+    for (int k = 0; k < W; ++k) {
+        const size_t src = r0 + __shfl_sync(0xffffffffu, par, k);
+        float4 *dst = reinterpret_cast<float4 *>(X + (r0 + k) * (2 * UNITS));
+        dst[lane] = __ldg(reinterpret_cast<const float4 *>(att + src * UNITS) + lane);
+        dst[32 + lane] = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + lane);
+    }
 }
 
 __global__ void init_state_kernel(float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent, int32_t *first_done,
@@ -312,6 +306,7 @@ int run(const Params &p, cudaStream_t s) {
     float *c0 = ATT + rows * 128, *c1 = c0 + rows * 128, *lp = c1 + rows * 128;
     int32_t *fin = reinterpret_cast<int32_t *>(lp + rows), *len = fin + rows, *tok = len + rows, *parent = tok + rows;
     int32_t *first_done = parent + rows;
+    RVB_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * rows * 256, s));          // step 0: attention = h = 0
     RVB_CUDA(cudaMemsetAsync(XA, 0, sizeof(float) * rows * 384, s));
     RVB_CUDA(cudaMemsetAsync(ATT, 0, sizeof(float) * rows * 128, s));
     RVB_CUDA(cudaMemsetAsync(c0, 0, sizeof(float) * rows * 128, s));
@@ -327,7 +322,6 @@ int run(const Params &p, cudaStream_t s) {
         const unsigned ab = (unsigned)((p.B + 3) / 4);
         {
             ProfScope ps(KK_DECODER, s);
-            gather_concat_kernel<<<(unsigned)((rows * 64 + 255) / 256), 256, 0, s>>>(ATT, XA, parent, X, rows, p.W);
             RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             cell_kernel<<<(unsigned)((rows * UNITS + 255) / 256), 256, 0, s>>>(Z, p.wtok, tok, parent, cin, cout, XA, rows, p.W);
             RVB_CHECK(gemm::run_tc(XA, p.wm_hiT, p.wm_loT, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, 3 * UNITS));
@@ -342,10 +336,10 @@ int run(const Params &p, cudaStream_t s) {
             ProfScope ps(KK_DECODER, s);
             RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
-                                                p.parent_ids, p.B, p.W, p.S, t);
+                                                p.parent_ids, p.B, p.W, p.S, t, XA, X);
             RVB_LAUNCH_CHECK();
         }
-        nl += 4;
+        nl += 3;
     }
     {
         ProfScope ps(KK_DECODER, s);
