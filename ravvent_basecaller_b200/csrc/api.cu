@@ -301,13 +301,16 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
         }
         RVB_CHECK(upload(m, &m->d_wtok, wtok));
         if (m->dec_wave) {
-            // [att-input rows ; U] as a [256,512] weight in Keras gate order, W_mem^T [128,256], W_att [384,128]
+            // [att-input rows ; U] as a [256,512] weight with gate columns in [unit][gate] order (the cell update is fused
+            // into that GEMM's epilogue, which sees 32 consecutive columns = 8 whole units); W_mem^T [128,256], W_att [384,128]
             std::vector<float> wcat((size_t)2 * UNITS * GATES), wtk((size_t)VOCAB * GATES), wmT((size_t)UNITS * ENC_OUT);
             for (int k = 0; k < 2 * UNITS; ++k)
-                for (int n = 0; n < GATES; ++n)
-                    wcat[(size_t)k * GATES + n] = k < UNITS ? Wd->data[(size_t)(VOCAB + k) * GATES + n] : Ud->data[(size_t)(k - UNITS) * GATES + n];
+                for (int n = 0; n < GATES; ++n) {
+                    const int col = (n % UNITS) * 4 + n / UNITS;
+                    wcat[(size_t)k * GATES + col] = k < UNITS ? Wd->data[(size_t)(VOCAB + k) * GATES + n] : Ud->data[(size_t)(k - UNITS) * GATES + n];
+                }
             for (int v = 0; v < VOCAB; ++v)
-                for (int n = 0; n < GATES; ++n) wtk[(size_t)v * GATES + n] = Wd->data[(size_t)v * GATES + n] + Bd->data[n];
+                for (int n = 0; n < GATES; ++n) wtk[(size_t)v * GATES + (n % UNITS) * 4 + n / UNITS] = Wd->data[(size_t)v * GATES + n] + Bd->data[n];
             for (int e = 0; e < ENC_OUT; ++e)
                 for (int d = 0; d < UNITS; ++d) wmT[(size_t)d * ENC_OUT + e] = Wm->data[(size_t)e * UNITS + d];
             float *tmp = nullptr;

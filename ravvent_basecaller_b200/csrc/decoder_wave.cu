@@ -6,8 +6,8 @@
 // tcgen05 projection kernel (K2, 3xTF32 = fp32 accuracy) instead of per-CTA FFMA loops that stall on L2 weight
 // streams.  Per step:
 //   (X[r] = [attention_prev[src(r)] | h_prev[src(r)]], src(r) = row of the parent beam, is written by the previous step's fc_search)
-//   GEMM            Z      = X . [W_att_in ; U]                              (K 256, N 512)
-//   cell            h, c   = LSTM(Z + W_token[token] + b, c_prev[src])       h -> XA[:, 0:128]
+//   GEMM + cell     h, c   = LSTM(X . [W_att_in ; U] + W_token[token] + b, c_prev[src])   (K 256, N 512; the cell update is
+//                            the GEMM's epilogue, gate columns in [unit][gate] order)     h -> XA[:, 0:128]
 //   GEMM            Q'     = h . W_mem^T                                     (K 128, N 256; folded Luong query)
 //   attention       ctx    = softmax_mask(values . q') . values              one warp per snippet, beams share the stream
 //   GEMM            A      = [h | ctx] . W_attention_layer                   (K 384, N 128)
@@ -21,25 +21,6 @@ namespace decw {
 constexpr int WMAX = 9;
 constexpr float F32_MIN = -3.4028234663852886e38f;
 
-__device__ __forceinline__ float fsig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) { return 2.0f * fsig(2.0f * x) - 1.0f; }
-
-// ---- LSTM cell pointwise: Z [rows,512] Keras gate order, wtok [7,512] (kernel row of the token + bias) ---------
-__global__ void cell_kernel(const float *__restrict__ Z, const float *__restrict__ wtok, const int32_t *__restrict__ tok,
-                            const int32_t *__restrict__ parent, const float *__restrict__ c_in, float *__restrict__ c_out,
-                            float *__restrict__ xa, long long rows, int W) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * UNITS) return;
-    const long long r = i >> 7; const int u = (int)(i & 127);
-    const long long src = (r / W) * W + parent[r];
-    const float *z = Z + r * GATES;
-    const float *wt = wtok + (size_t)tok[r] * GATES;
-    const float zi = z[u] + __ldg(wt + u), zf = z[UNITS + u] + __ldg(wt + UNITS + u);
-    const float zg = z[2 * UNITS + u] + __ldg(wt + 2 * UNITS + u), zo = z[3 * UNITS + u] + __ldg(wt + 3 * UNITS + u);
-    const float c = fsig(zf) * c_in[src * UNITS + u] + fsig(zi) * ftanh(zg);
-    c_out[i] = c;
-    xa[r * (3 * UNITS) + u] = fsig(zo) * ftanh(c);
-}
 
 // ---- packed fp32 pairs: sm_100a executes two fp32 FMAs per issue slot (fma.rn.f32x2 -> FFMA2); nvcc does not pair them
 //      on its own, and the attention kernel below is issue bound on exactly these FMAs -------------------------------
@@ -322,8 +303,8 @@ int run(const Params &p, cudaStream_t s) {
         const unsigned ab = (unsigned)((p.B + 3) / 4);
         {
             ProfScope ps(KK_DECODER, s);
-            RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
-            cell_kernel<<<(unsigned)((rows * UNITS + 255) / 256), 256, 0, s>>>(Z, p.wtok, tok, parent, cin, cout, XA, rows, p.W);
+            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W};      // cell update fused into the GEMM epilogue
+            RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, 0, &ce));
             RVB_CHECK(gemm::run_tc(XA, p.wm_hiT, p.wm_loT, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, 3 * UNITS));
         }
         {
@@ -339,7 +320,7 @@ int run(const Params &p, cudaStream_t s) {
                                                 p.parent_ids, p.B, p.W, p.S, t, XA, X);
             RVB_LAUNCH_CHECK();
         }
-        nl += 3;
+        nl += 2;
     }
     {
         ProfScope ps(KK_DECODER, s);

@@ -50,8 +50,18 @@ int run_simt(const float *A, const float *Bm, const float *bias, float *C, long 
 // tcgen05 path: WhiT / WloT are the [N,K] tf32 hi / remainder parts made by prepare_weights
 int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaStream_t s);
 // lda: row pitch of A in elements (0 = K)
+// Optional fused epilogue of the wave-level decoder's cell GEMM (N = 512 gate columns in [unit][gate] order): instead of
+// storing Z, each accumulator row adds the token's kernel row, runs the LSTM cell update against c_in[parent row] and
+// writes c_out[row, unit] and h into xa[row, 0:128] (row stride 384).
+struct CellEpilogue {
+    const float *wtok;          // [vocab][512]: input-kernel row of the token + bias, [unit][gate] order
+    const int32_t *tok, *parent;
+    const float *c_in;
+    float *c_out, *xa;
+    int W;                      // beams per snippet (parent indices are relative to the snippet's first row)
+};
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
-           int precision, int *abort_flag, cudaStream_t s, long long lda = 0);
+           int precision, int *abort_flag, cudaStream_t s, long long lda = 0, const CellEpilogue *cell = nullptr);
 bool tc_available();
 // fp16-plane path (A produced as hi/lo planes by K3): all operands fp16, 3 passes on the fp16 pipe
 int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t s);

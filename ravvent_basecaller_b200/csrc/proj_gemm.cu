@@ -115,10 +115,14 @@ int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaSt
 }
 
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
-           int precision, int *abort_flag, cudaStream_t stream, long long lda) {
+           int precision, int *abort_flag, cudaStream_t stream, long long lda, const CellEpilogue *cell) {
     if (M <= 0) return RVB_OK;
     if (N % 128 != 0 || K % tc::BK != 0) return fail(RVB_ERR_ARG, "gemm_tc: N %% 128 and K %% 32 must be 0 (N=%d K=%d)", N, K);
     const bool three = (precision == RVB_PREC_FP32);
+    if (cell != nullptr) {
+        if (N != GATES || !three) return fail(RVB_ERR_ARG, "gemm_tc: the fused cell epilogue needs N = 512 and the fp32-parity mode");
+        return tc::launch_persistent<3, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda, false, cell);
+    }
     static const bool legacy = getenv("RVB_GEMM_NONPERSISTENT") != nullptr;      // A/B switch for profiling
     if (N % 256 == 0 && !legacy) return three ? tc::launch_persistent<3, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda)
                                               : tc::launch_persistent<1, false>(A, nullptr, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda);

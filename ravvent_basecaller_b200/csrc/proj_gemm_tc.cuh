@@ -317,6 +317,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ float cell_sig(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float cell_tanh(float x) { return 2.0f * cell_sig(2.0f * x) - 1.0f; }
+
 // MC (fp16-plane encoder GEMM): CTAs are launched as clusters of two that walk the SAME column tile on adjacent row
 // tiles in lockstep; each loads half of the W stage and multicasts it to both, so a CTA pulls 64 KB instead of 96 KB per
 // stage out of L2 (the operand fill, not the MMA pipe, bounded the single-CTA form).  The MMAs stay cta_group::1; a
@@ -326,7 +329,8 @@ __global__ void __launch_bounds__(PTHREADS, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_alo,
                           const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                           const __grid_constant__ CUtensorMap map_c,
-                          const float *__restrict__ bias, long long M, int N, int K, int *abort_flag, float *__restrict__ c_blocked) {
+                          const float *__restrict__ bias, long long M, int N, int K, int *abort_flag, float *__restrict__ c_blocked,
+                          const CellEpilogue cell) {
     using cfg = PCfg<NPASS, F16IN, PAIR>;
     constexpr bool MC = PAIR == 1, SM2 = PAIR == 2;
     extern __shared__ unsigned char smem_dyn[];
@@ -524,6 +528,31 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     }
                     continue;
                 }
+                if (cell.xa != nullptr) {                  // fused LSTM cell of the wave-level decoder: 32 columns = 8 units x (i, f, g, o)
+                    const long long R = m_tile * BM + row;
+                    if (R < M) {
+                        const int col0 = n_tile * PBN + c0, u0 = col0 >> 2;
+                        const float4 *tk = reinterpret_cast<const float4 *>(cell.wtok + (size_t)__ldg(cell.tok + R) * N + col0);
+                        const long long src = (R / cell.W) * cell.W + __ldg(cell.parent + R);
+                        const float4 ca = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0));
+                        const float4 cb4 = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0 + 4));
+                        const float cin[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
+                        float cn[8], hn[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 tv = __ldg(tk + u);
+                            const float zi = __uint_as_float(r[4 * u]) + tv.x, zf = __uint_as_float(r[4 * u + 1]) + tv.y;
+                            const float zg = __uint_as_float(r[4 * u + 2]) + tv.z, zo = __uint_as_float(r[4 * u + 3]) + tv.w;
+                            cn[u] = cell_sig(zf) * cin[u] + cell_sig(zi) * cell_tanh(zg);
+                            hn[u] = cell_sig(zo) * cell_tanh(cn[u]);
+                        }
+                        float4 *co = reinterpret_cast<float4 *>(cell.c_out + R * 128 + u0);
+                        co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                        float4 *ho = reinterpret_cast<float4 *>(cell.xa + R * 384 + u0);
+                        ho[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); ho[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                    }
+                    continue;
+                }
                 unsigned char *cb = cstage + (NGRP == 2 ? grp : (chunk_ctr & 1)) * CSTAGE_BYTES;
                 if (et == 0) {                             // the store that last used cb has finished reading it
                     if (NGRP == 2) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -615,8 +644,11 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
 // F16IN: A (and W) are given as fp16 hi / lo planes ([M,K] / [N,K] row-major), K-elements per stage = 64.
 template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
-                      long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0, bool blocked_out = false) {
+                      long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0, bool blocked_out = false,
+                      const CellEpilogue *cell_epi = nullptr) {
     float *c_blocked = blocked_out ? C : nullptr;
+    CellEpilogue cell{};
+    if (cell_epi != nullptr) cell = *cell_epi;
     constexpr int PAIRED = (F16IN && NPASS == 3) ? 2 : 0;         // cluster form used for the big encoder GEMM
     using cfg = PCfg<NPASS, F16IN, 0>;
     using cfgp = PCfg<NPASS, F16IN, PAIRED>;
@@ -650,12 +682,12 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
         ProfScope ps(KK_GEMM, stream);
-        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked));
+        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell));
     } else {
         RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
         ProfScope ps(KK_GEMM, stream);
-        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked);
+        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell);
     }
     RVB_LAUNCH_CHECK();
     count_launch();
