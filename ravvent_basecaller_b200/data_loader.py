@@ -145,3 +145,26 @@ def load_data_from_single_signal_label(signal_path, label_path, stride, as_numpy
     if as_numpy:
         return rs.cpu().numpy(), es.cpu().numpy(), tokens
     return rs, es, tokens
+
+
+def create_files_info(files_dir, stride=6, verbose=True, device=None):
+    """data_loader.create_files_info (data_loader.py:129-156): index every `.signal` / `.label` pair of a directory with
+    its snippet count into `files_info.snippets.stride_<stride>.json` (the list the evaluators iterate over)."""
+    import json
+    from pathlib import Path
+    d = Path(files_dir)
+    files_info_path = d / f'files_info.snippets.stride_{stride}.json'
+    signals = sorted(p for p in d.iterdir() if p.suffix == '.signal')
+    labels = sorted(p for p in d.iterdir() if p.suffix == '.label')
+    files_info = []
+    for signal_path, label_path in zip(signals, labels):
+        raw_snippets, _, _ = load_data_from_single_signal_label(signal_path, label_path, stride, device=device)
+        if verbose:
+            print('{}'.format(signal_path.stem))
+        files_info.append({'signal_path': signal_path.as_posix(), 'label_path': label_path.as_posix(),
+                           'snippets_num': int(raw_snippets.shape[0])})
+        with open(files_info_path, 'wt') as fi:
+            json.dump(files_info, fi, indent=2)
+    with open(files_info_path, 'wt') as fi:
+        json.dump(files_info, fi, indent=2)
+    return files_info_path

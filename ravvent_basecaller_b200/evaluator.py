@@ -1,5 +1,7 @@
 """RavventPerformanceEvaluator -- the reference's timed read loop (ravvent_performance_evaluator.py:13-148)
-over the B200 path: `.signal` / `.label` in, one merged read and the timing dictionary out.
+over the B200 path: `.signal` / `.label` in, one merged read and the timing dictionary out -- and
+RavventMappingEvaluator (ravvent_mapping_evaluator.py:20-110): the same read written as FASTA / FASTQ and
+mapped with minimap2 when that binary is installed.
 
 Same method names, arguments and result keys as the reference, so its result files and
 `compute_total_results` keep working.  Differences that do not change results: snippets stay on the
@@ -9,6 +11,9 @@ device between the loader, the basecaller and the merger; `beam_width` is a cons
 from __future__ import annotations
 
 import json
+import shlex
+import shutil
+import subprocess
 from pathlib import Path
 from timeit import default_timer as timer
 
@@ -186,3 +191,59 @@ class RavventPerformanceEvaluator():
             with open(results_path, 'wt') as f:
                 json.dump(results, f, indent=2)
         return results
+
+
+class RavventMappingEvaluator(RavventPerformanceEvaluator):
+    """ravvent_mapping_evaluator.py:20-110.  run() basecalls and stitches one read, writes the reference as FASTA and
+    the prediction as FASTQ, maps them with `minimap2 -x map-ont -c` and returns the identity dictionary.  The file
+    writers and the PAF reader are static so they can be used (and tested) without a GPU."""
+
+    def __init__(self, merger_scores_id=0, beam_width=5, device=None, precision='fp32', work_dir='temp'):
+        super().__init__(merger_scores_id, beam_width, device, precision)
+        self.work_dir = Path(work_dir)
+
+    @staticmethod
+    def _create_fasta(seq, fname):
+        with open(fname, 'wt') as f:
+            f.write(f'>{seq[:10]}\n{seq}')
+
+    @staticmethod
+    def _create_fastq(seq, fname):
+        with open(fname, 'wt') as f:
+            f.write(f'@{seq[:10]}\n')
+            f.write(seq + '\n')
+            f.write('+\n')
+            f.write('!' * len(seq))
+
+    @staticmethod
+    def _run_minimap(ref_path, pred_path, out_path):
+        if shutil.which('minimap2') is None:
+            raise FileNotFoundError("minimap2 is not installed (ravvent_mapping_evaluator.py:86 shells out to it)")
+        cmd = f'minimap2 -x map-ont -c {ref_path} {pred_path}'
+        with open(out_path, 'wt') as f:
+            subprocess.run(shlex.split(cmd), stdout=f, check=False)
+
+    @staticmethod
+    def _read_mapping_identity(mapping_path):
+        matches = total_blocks_len = read_length = 0
+        with open(mapping_path, 'rt') as paf:
+            for line in paf:
+                parts = line.strip().split('\t')
+                if len(parts) < 11:
+                    continue
+                read_length = int(parts[1])
+                matches += int(parts[9])
+                total_blocks_len += int(parts[10])
+        return {'read_length': read_length, 'matches': matches, 'total_block_len': total_blocks_len,
+                'identity': matches / total_blocks_len if total_blocks_len != 0 else 0.}
+
+    def run(self, signal_data_source, chunk_size=1024):
+        label_path = Path(signal_data_source).with_suffix('.label')
+        ref_seq = ''.join(list(np.loadtxt(label_path, dtype='object', ndmin=2)[:, 2]))
+        merged_seq = super().run(signal_data_source, chunk_size)['merged_seq']
+        self.work_dir.mkdir(parents=True, exist_ok=True)
+        fasta_path, fastq_path, mapping_path = (self.work_dir / n for n in ('ref.fasta', 'pred.fastq', 'mapping.paf'))
+        self._create_fasta(ref_seq, fasta_path)
+        self._create_fastq(merged_seq, fastq_path)
+        self._run_minimap(fasta_path, fastq_path, mapping_path)
+        return self._read_mapping_identity(mapping_path)
