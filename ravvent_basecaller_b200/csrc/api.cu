@@ -69,6 +69,7 @@ struct rvb_model {
     float *d_wg1 = nullptr, *d_b1 = nullptr;
     // wave-level beam decoder (decoder_wave.cu): tf32 hi/lo transposed weights + Keras-order token rows + workspace
     float *dw_wg[2] = {nullptr, nullptr}, *dw_wm[2] = {nullptr, nullptr}, *dw_wa[2] = {nullptr, nullptr}, *dw_wtok = nullptr, *dw_ws = nullptr;
+    uint16_t *dw_wg16[2] = {nullptr, nullptr}, *dw_wm16[2] = {nullptr, nullptr};
     size_t dw_ws_rows = 0;
     bool dec_wave = false;
     float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
@@ -314,14 +315,20 @@ extern "C" int rvb_model_finalize(rvb_model_t *m) {
             for (int e = 0; e < ENC_OUT; ++e)
                 for (int d = 0; d < UNITS; ++d) wmT[(size_t)d * ENC_OUT + e] = Wm->data[(size_t)e * UNITS + d];
             float *tmp = nullptr;
-            auto prep = [&](const std::vector<float> &w, int K, int N, float **pair) -> int {
+            auto prep = [&](const std::vector<float> &w, int K, int N, float **pair, uint16_t **pair16 = nullptr) -> int {
                 RVB_CHECK(upload(m, &tmp, w));
                 RVB_CHECK(dmalloc(m, &pair[0], w.size()));
                 RVB_CHECK(dmalloc(m, &pair[1], w.size()));
-                return gemm::prepare_weights(tmp, pair[0], pair[1], K, N, nullptr);
+                RVB_CHECK(gemm::prepare_weights(tmp, pair[0], pair[1], K, N, nullptr));
+                if (pair16 != nullptr) {        // fp16 hi / lo planes of the same weight: the GEMM then runs on the fp16 pipe
+                    RVB_CHECK(dmalloc(m, &pair16[0], w.size()));
+                    RVB_CHECK(dmalloc(m, &pair16[1], w.size()));
+                    RVB_CHECK(gemm::prepare_weights_f16(tmp, pair16[0], pair16[1], K, N, nullptr));
+                }
+                return RVB_OK;
             };
-            RVB_CHECK(prep(wcat, 2 * UNITS, GATES, m->dw_wg));
-            RVB_CHECK(prep(wmT, UNITS, ENC_OUT, m->dw_wm));
+            RVB_CHECK(prep(wcat, 2 * UNITS, GATES, m->dw_wg, m->dw_wg16));
+            RVB_CHECK(prep(wmT, UNITS, ENC_OUT, m->dw_wm, m->dw_wm16));
             RVB_CHECK(prep(Wa->data, UNITS + ENC_OUT, UNITS, m->dw_wa));
             RVB_CHECK(upload(m, &m->dw_wtok, wtk));
         }
@@ -506,7 +513,8 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             decw::Params q{};
             q.values = m->enc_out; q.mask = m->mask;
             q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
-            q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
+            q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];
+            q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
             q.B = nb; q.Tm = Tm; q.W = W; q.S = S;
             q.ids = d_ids + (size_t)b0 * S * W; q.scores = d_scores + (size_t)b0 * S * W;
             q.step_ids = d_step_ids ? d_step_ids + (size_t)b0 * S * W : m->step_ids;

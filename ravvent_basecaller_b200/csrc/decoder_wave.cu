@@ -13,6 +13,8 @@
 //   GEMM            A      = [h | ctx] . W_attention_layer                   (K 384, N 128)
 //   fc_search       logits = A . fc + b; tfa _beam_search_step (warp top-k); per-step outputs, next token / parent, next X
 // and after the last step gather_tree.  The beam reorder never moves state: consumers read rows through src(r).
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace rvb {
@@ -161,7 +163,8 @@ __device__ __forceinline__ void warp_argmax(float &v, int &i) {
 __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict__ att, const float *__restrict__ wfc, const float *__restrict__ bfc,
                                                         float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent,
                                                         int32_t *first_done, float *scores, int32_t *step_ids, int32_t *parent_ids,
-                                                        int B, int W, int S, int t, const float *__restrict__ xa, float *__restrict__ X) {
+                                                        int B, int W, int S, int t, const float *__restrict__ xa, float *__restrict__ X,
+                                                        uint16_t *__restrict__ x_hi, uint16_t *__restrict__ x_lo) {
     __shared__ float a_s[4][WMAX * UNITS];
     __shared__ float lg_s[4][WMAX * 8];
     __shared__ float wfc_s[UNITS * VOCAB];
@@ -232,9 +235,23 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     // input of the next step's cell GEMM, gathered through the parents chosen just now: X[r] = [attention[src] | h[src]]
     for (int k = 0; k < W; ++k) {
         const size_t src = r0 + __shfl_sync(0xffffffffu, par, k);
-        float4 *dst = reinterpret_cast<float4 *>(X + (r0 + k) * (2 * UNITS));
-        dst[lane] = __ldg(reinterpret_cast<const float4 *>(att + src * UNITS) + lane);
-        dst[32 + lane] = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + lane);
+        const float4 va = __ldg(reinterpret_cast<const float4 *>(att + src * UNITS) + lane);
+        const float4 vh = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + lane);
+        if (x_hi != nullptr) {                 // fp16 hi / lo planes (the cell GEMM runs on the fp16 pipe)
+            auto put = [&](const float4 v, size_t o) {
+                const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+                *reinterpret_cast<uint2 *>(x_hi + o) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                *reinterpret_cast<uint2 *>(x_lo + o) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+            };
+            put(va, (r0 + k) * (2 * UNITS) + 4 * lane);
+            put(vh, (r0 + k) * (2 * UNITS) + UNITS + 4 * lane);
+        } else {
+            float4 *dst = reinterpret_cast<float4 *>(X + (r0 + k) * (2 * UNITS));
+            dst[lane] = va;
+            dst[32 + lane] = vh;
+        }
     }
 }
 
@@ -287,6 +304,11 @@ int run(const Params &p, cudaStream_t s) {
     float *c0 = ATT + rows * 128, *c1 = c0 + rows * 128, *lp = c1 + rows * 128;
     int32_t *fin = reinterpret_cast<int32_t *>(lp + rows), *len = fin + rows, *tok = len + rows, *parent = tok + rows;
     int32_t *first_done = parent + rows;
+    // fp16-plane operands share the X / Z regions: X = [hi plane | lo plane] of [rows][256] halves, Z holds the h planes
+    static const bool f16_off = getenv("RVB_DECODER_GEMM") && strcmp(getenv("RVB_DECODER_GEMM"), "tf32") == 0;
+    const bool f16 = p.wg16_hi != nullptr && p.wm16_hi != nullptr && !f16_off;
+    uint16_t *x_hi = reinterpret_cast<uint16_t *>(X), *x_lo = x_hi + rows * 256;
+    uint16_t *h_hi = reinterpret_cast<uint16_t *>(Z), *h_lo = h_hi + rows * 128;
     RVB_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * rows * 256, s));          // step 0: attention = h = 0
     RVB_CUDA(cudaMemsetAsync(XA, 0, sizeof(float) * rows * 384, s));
     RVB_CUDA(cudaMemsetAsync(ATT, 0, sizeof(float) * rows * 128, s));
@@ -303,9 +325,15 @@ int run(const Params &p, cudaStream_t s) {
         const unsigned ab = (unsigned)((p.B + 3) / 4);
         {
             ProfScope ps(KK_DECODER, s);
-            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W};      // cell update fused into the GEMM epilogue
-            RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, 0, &ce));
-            RVB_CHECK(gemm::run_tc(XA, p.wm_hiT, p.wm_loT, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, 3 * UNITS));
+            // cell update fused into the GEMM epilogue; with fp16 weight planes both GEMMs run on the fp16 pipe (3 split passes)
+            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr};
+            if (f16) {
+                RVB_CHECK(gemm::run_tc_f16(x_hi, x_lo, p.wg16_hi, p.wg16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce));
+                RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s));
+            } else {
+                RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, 0, &ce));
+                RVB_CHECK(gemm::run_tc(XA, p.wm_hiT, p.wm_loT, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, 3 * UNITS));
+            }
         }
         {
             ProfScope ps(KK_ATTENTION, s);
@@ -317,7 +345,7 @@ int run(const Params &p, cudaStream_t s) {
             ProfScope ps(KK_DECODER, s);
             RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
-                                                p.parent_ids, p.B, p.W, p.S, t, XA, X);
+                                                p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr);
             RVB_LAUNCH_CHECK();
         }
         nl += 2;

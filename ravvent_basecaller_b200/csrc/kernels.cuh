@@ -59,6 +59,7 @@ struct CellEpilogue {
     const float *c_in;
     float *c_out, *xa;
     int W;                      // beams per snippet (parent indices are relative to the snippet's first row)
+    uint16_t *h_hi, *h_lo;      // optional fp16 hi / lo planes of h, [row][128]: the A operand of the query GEMM
 };
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
            int precision, int *abort_flag, cudaStream_t s, long long lda = 0, const CellEpilogue *cell = nullptr);
@@ -67,7 +68,7 @@ bool tc_available();
 int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t s);
 int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cudaStream_t s);
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
-               int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false);
+               int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false, const CellEpilogue *cell = nullptr);
 }  // namespace gemm
 
 namespace dec {     // K4 + K5, decoder.cu
@@ -99,10 +100,11 @@ namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >
 struct Params {
     const float *values;        // [B,Tm,256]
     const uint8_t *mask;        // [B,Tm]
-    const float *wg_hiT, *wg_loT;   // tf32 hi / lo of [att-input rows ; recurrent kernel], transposed [512,256], Keras gate order
+    const float *wg_hiT, *wg_loT;   // tf32 hi / lo of [att-input rows ; recurrent kernel], transposed [512,256], [unit][gate] columns
     const float *wm_hiT, *wm_loT;   // W_mem^T as a [K=128, N=256] weight, transposed [256,128]
     const float *wa_hiT, *wa_loT;   // attention layer [384,128], transposed [128,384]
-    const float *wtok;          // [7][512] kernel row of token v + bias, Keras gate order
+    const void *wg16_hi, *wg16_lo, *wm16_hi, *wm16_lo;   // fp16 hi / lo planes of the first two (transposed); nullptr: tf32 path
+    const float *wtok;          // [7][512] kernel row of token v + bias, [unit][gate] columns
     const float *wfc, *bfc;     // [128][7], [7]
     int B, Tm, W, S;
     int32_t *ids;               // predicted_ids [B,S,W]

@@ -16,6 +16,7 @@
 // kernel raises a flag and drains instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "kernels.cuh"
 
@@ -550,6 +551,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
                         float4 *ho = reinterpret_cast<float4 *>(cell.xa + R * 384 + u0);
                         ho[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); ho[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                        if (cell.h_hi != nullptr) {          // fp16 hi / lo planes of h for the query GEMM
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const __half2 hh = __floats2half2_rn(hn[2 * i], hn[2 * i + 1]);
+                                const float2 hf = __half22float2(hh);
+                                const __half2 ll = __floats2half2_rn(hn[2 * i] - hf.x, hn[2 * i + 1] - hf.y);
+                                hi[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                                lo[i] = *reinterpret_cast<const uint32_t *>(&ll);
+                            }
+                            *reinterpret_cast<uint4 *>(cell.h_hi + R * 128 + u0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4 *>(cell.h_lo + R * 128 + u0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
                     }
                     continue;
                 }
