@@ -6,9 +6,11 @@
 //
 // A read is a strictly sequential chain (snippet i is aligned against the last 25 bases of everything merged so
 // far), reads are independent: ONE WARP PER READ.  Per snippet:
-//   1. the 26 x 26 affine score / trace matrices are filled by anti-diagonals, lane = row (float64, the same
-//      operations in the same order as the restated pairwise2 "fast" recurrence; this file is built with
-//      -fmad=false so no a*b+c is contracted) -- 49 dependent steps instead of 625;
+//   1. the 26 x 26 affine score matrices (best / gap-in-A / gap-in-B) are filled by anti-diagonals, lane = row (float64,
+//      the same operations in the same order as the restated pairwise2 "fast" recurrence; this file is built with
+//      -fmad=false so no a*b+c is contracted) -- 49 dependent steps instead of 625; pairwise2's trace matrix (seven rounded
+//      comparisons per cell) is computed in a second pass in which the 625 cells are independent of each other, so it
+//      runs 32 cells wide with full instruction-level parallelism instead of sitting in the recurrence's dependency chain;
 //   2. lanes mark the admissible start cells in parallel (within 5e-4 of the best score, positive, ending on a
 //      match, not a zero-score extension of another start);
 //   3. lane 0 runs pairwise2's iterative back-trace with an explicit stack in shared memory (last start first; per
@@ -25,7 +27,7 @@ constexpr int OVL = 25;                 // merger.py:150
 constexpr int DIM = OVL + 1;
 constexpr int MAXCOL = 64;              // gapped alignment columns (<= 2 * OVL)
 constexpr int STACK = 160;
-constexpr int WARPS = 4;
+constexpr int WARPS = 2;
 
 struct ScoreSet { double match[4][4]; double open, extend; };
 
@@ -35,6 +37,7 @@ struct StackEntry { uint8_t n, row, col, col_gap, trace, gap_from, gap_dir, pad;
 
 struct WarpSmem {
     double score[DIM][DIM];
+    double rowsc[DIM][DIM], colsc[DIM][DIM];   // running gap scores after each cell (inputs of the trace pass)
     uint8_t trace[DIM][DIM];
     uint32_t valid[DIM];                // bit c of valid[r]: admissible start cell
     StackEntry stack[STACK];
@@ -58,14 +61,12 @@ __device__ __forceinline__ double affine_penalty(int length, double open, double
     return p;
 }
 
-// ---- 1. score / trace matrices, lane = row - 1 ----------------------------------------------------------------------
+// ---- 1. score matrices, lane = row - 1 ---------------------------------------------------------------------------------
 __device__ double fill_matrices(WarpSmem &w, const ScoreSet &ss, int len_a, int len_b, int lane) {
     const double open = ss.open, extend = ss.extend;
     const double first_gap = affine_penalty(1, open, extend);
     const int row = lane + 1;
     const bool live = row <= len_a;
-    for (int i = lane; i < DIM * DIM; i += 32) { (&w.score[0][0])[i] = 0.0; (&w.trace[0][0])[i] = 0; }
-    __syncwarp();
     const int a = live ? w.seq_a[lane] : 0;
     double row_score = affine_penalty(row, 2.0 * open, extend);
     double s_left = 0.0;                // score[row][col - 1]
@@ -91,14 +92,9 @@ __device__ double fill_matrices(WarpSmem &w, const ScoreSet &ss, int len_a, int 
             const double best = fmax(fmax(nogap, col_score), row_score);
             local_max = fmax(local_max, best);
             const double sc = best < 0.0 ? 0.0 : best;
-            const int rs = rint1000(row_score), cs = rint1000(col_score), bs = rint1000(best);
-            const int row_trace = (rint1000(row_open) == rs ? 1 : 0) + (rint1000(row_extend) == rs ? 8 : 0);
-            const int col_trace = (rint1000(col_open) == cs ? 4 : 0) + (rint1000(col_extend) == cs ? 16 : 0);
-            int t = rint1000(nogap) == bs ? 2 : 0;
-            if (rs == bs) t += row_trace;
-            if (cs == bs) t += col_trace;
             w.score[row][col] = sc;
-            w.trace[row][col] = best <= 0.0 ? 0 : (uint8_t)t;
+            w.rowsc[row][col] = row_score;
+            w.colsc[row][col] = col_score;
             s_left = sc;
             s_cur = sc;
             cs_cur = col_score;
@@ -112,8 +108,44 @@ __device__ double fill_matrices(WarpSmem &w, const ScoreSet &ss, int len_a, int 
     return local_max;
 }
 
+// pairwise2's trace bits of one cell (1 open gap in A, 2 match, 4 open gap in B, 8 extend A, 16 extend B; 0 = None),
+// recomputed from the three score matrices with the recurrence's own operations.
+__device__ int trace_bits(const WarpSmem &w, const ScoreSet &ss, int len_a, int len_b, int row, int col) {
+    if (row < 1 || col < 1) return 0;
+    const double open = ss.open, extend = ss.extend;
+    const double first_gap = affine_penalty(1, open, extend);
+    const double nogap = w.score[row - 1][col - 1] + ss.match[w.seq_a[row - 1]][w.seq_b[col - 1]];
+    const double s_left = w.score[row][col - 1], up = w.score[row - 1][col];
+    const double rs_prev = (col == 1) ? affine_penalty(row, 2.0 * open, extend) : w.rowsc[row][col - 1];
+    const double cs_prev = (row == 1) ? affine_penalty(col, 2.0 * open, extend) : w.colsc[row - 1][col];
+    double row_open, row_extend, col_open, col_extend;
+    if (row == len_a) { row_open = s_left; row_extend = rs_prev; }
+    else { row_open = s_left + first_gap; row_extend = rs_prev + extend; }
+    const double row_score = fmax(row_open, row_extend);
+    if (col == len_b) { col_open = up; col_extend = cs_prev; }
+    else { col_open = up + first_gap; col_extend = cs_prev + extend; }
+    const double col_score = fmax(col_open, col_extend);
+    const double best = fmax(fmax(nogap, col_score), row_score);
+    if (best <= 0.0) return 0;
+    const int rs = rint1000(row_score), cs = rint1000(col_score), bs = rint1000(best);
+    const int row_trace = (rint1000(row_open) == rs ? 1 : 0) + (rint1000(row_extend) == rs ? 8 : 0);
+    const int col_trace = (rint1000(col_open) == cs ? 4 : 0) + (rint1000(col_extend) == cs ? 16 : 0);
+    int t = rint1000(nogap) == bs ? 2 : 0;
+    if (rs == bs) t += row_trace;
+    if (cs == bs) t += col_trace;
+    return t;
+}
+__device__ void trace_pass(WarpSmem &w, const ScoreSet &ss, int len_a, int len_b, int lane) {
+    const int n = len_a * len_b;
+    for (int i = lane; i < n; i += 32) {
+        const int row = i / len_b + 1, col = i % len_b + 1;
+        w.trace[row][col] = (uint8_t)trace_bits(w, ss, len_a, len_b, row, col);
+    }
+    __syncwarp();
+}
+
 // ---- 2. admissible start cells ---------------------------------------------------------------------------------------
-__device__ void mark_starts(WarpSmem &w, int len_a, int len_b, double best, int lane) {
+__device__ void mark_starts(WarpSmem &w, const ScoreSet &ss, int len_a, int len_b, double best, int lane) {
     const int row = lane + 1;
     uint32_t bits = 0;
     if (row <= len_a) {
@@ -128,11 +160,11 @@ __device__ void mark_starts(WarpSmem &w, int len_a, int len_b, double best, int 
             bits |= 1u << col;
         }
     }
-    __syncwarp();                       // every lane has read its neighbours' traces before any is overwritten
+    __syncwarp();                       // every lane has read the traces it needs before any is overwritten
     if (row < DIM) {
         w.valid[row] = bits;
         for (int col = 1; col <= len_b; ++col)
-            if ((bits >> col) & 1u) w.trace[row][col] = 2;
+            if ((bits >> col) & 1u) w.trace[row][col] = 2;       // pairwise2 does the same to every admissible start
     }
     __syncwarp();
 }
@@ -264,6 +296,8 @@ __global__ void __launch_bounds__(32 * WARPS) merge_kernel(const uint8_t *__rest
     if (read >= n_reads) return;
     WarpSmem &w = smem[threadIdx.x >> 5];
     if (lane == 0) w.error = 0;
+    for (int i = lane; i < DIM; i += 32) { w.score[0][i] = 0.0; w.score[i][0] = 0.0; w.trace[0][i] = 0; w.trace[i][0] = 0; }    // never written afterwards
+    __syncwarp();
     const int s0 = read_off[read], s1 = read_off[read + 1];
     uint8_t *mseq = seq_out + (size_t)s0 * steps;
     float *mlog = log_out + (size_t)s0 * steps;
@@ -286,7 +320,8 @@ __global__ void __launch_bounds__(32 * WARPS) merge_kernel(const uint8_t *__rest
             if (lane < len_b) { w.seq_b[lane] = aseq[lane]; w.log_b[lane] = alog[lane]; }
             __syncwarp();
             const double best = fill_matrices(w, ss, len_a, len_b, lane);
-            mark_starts(w, len_a, len_b, best, lane);
+            trace_pass(w, ss, len_a, len_b, lane);
+            mark_starts(w, ss, len_a, len_b, best, lane);
             if (lane == 0) {
                 backtrace(w, ss, len_a, len_b, best);
                 const int n = w.n_cols;
