@@ -248,7 +248,7 @@ def greedy_search(w, enc_output, mask, max_output_len, dec_units=128, decoder_de
 # --------------------------------------------------------------------------
 # beam search (A.5)
 # --------------------------------------------------------------------------
-def beam_step(step_log_probs, log_probs, finished, lengths, end_token=TOKEN_END):
+def beam_step(step_log_probs, log_probs, finished, lengths, end_token=TOKEN_END, with_margin=False):
     """_beam_search_step on already log-softmaxed rows.
     step_log_probs [B,W,V] ; log_probs [B,W] ; finished [B,W] bool ; lengths [B,W] int64.
     -> scores, word, parent, next_log_probs, next_finished, next_lengths."""
@@ -265,7 +265,23 @@ def beam_step(step_log_probs, log_probs, finished, lengths, end_token=TOKEN_END)
     prev_fin = np.take_along_axis(finished, parent, axis=-1)
     next_finished = prev_fin | (word == end_token)
     next_lengths = np.take_along_axis(lengths, parent, axis=-1) + (~prev_fin).astype(np.int64)
+    if with_margin:
+        return scores, word, parent, scores.copy(), next_finished, next_lengths, topk_margin(total, W)
     return scores, word, parent, scores.copy(), next_finished, next_lengths
+
+
+def topk_margin(total, W):
+    """Smallest gap between neighbours among the W+1 best candidates of each row: how close the step was to a
+    different selection OR a different slot order.  Pairs of exactly equal values are resolved by index in every
+    implementation (top_k is stable) and pairs at the -inf / dtype.min level are not real candidates: both are
+    skipped, except finite exact ties, which count as margin 0 (another summation order may split them)."""
+    srt = -np.sort(-total.astype(np.float64), axis=-1)[:, :W + 1]
+    a, b = srt[:, :-1], srt[:, 1:]
+    with np.errstate(invalid="ignore"):
+        gap = a - b
+    real = np.isfinite(a) & np.isfinite(b) & (b > -1e30)
+    gap = np.where(real, gap, np.inf)
+    return gap.min(axis=-1)
 
 
 def gather_tree(step_ids, parent_ids, max_sequence_lengths, end_token=TOKEN_END):
@@ -291,9 +307,10 @@ def gather_tree(step_ids, parent_ids, max_sequence_lengths, end_token=TOKEN_END)
 
 
 def beam_search(w, enc_output, mask, beam_width, max_output_len, dec_units=128, decoder_depth=1,
-                dtype=np.float32, full_length=False, return_all=False):
+                dtype=np.float32, full_length=False, return_all=False, return_margins=False):
     """BeamSearchDecoder under dynamic_decode + finalize.
-    -> (predicted_ids[:, :, 0] [B,T] int32, scores[:, :, 0] [B,T])."""
+    -> (predicted_ids[:, :, 0] [B,T] int32, scores[:, :, 0] [B,T]).
+    return_all: all beams + the raw per-step ids / parents; return_margins adds margins [B,T] (topk_margin per step)."""
     wc = cast_weights(w, dtype)
     B, Tm, _ = enc_output.shape
     W = int(beam_width)
@@ -309,12 +326,13 @@ def beam_search(w, enc_output, mask, beam_width, max_output_len, dec_units=128, 
     finished[:, 0] = False
     lengths = np.zeros((B, W), dtype=np.int64)
     all_done = bool(0 >= S)
-    s_scores, s_ids, s_par = [], [], []
+    s_scores, s_ids, s_par, s_margin = [], [], [], []
     t = 0
     while (full_length and t < S) or (not full_length and not all_done):
         logits, state, _ = decoder_step(wc, tokens, state, keys, values, maskt, decoder_depth)
         slp = log_softmax(logits.reshape(B, W, -1))
-        scores, word, parent, log_probs, finished, lengths = beam_step(slp, log_probs, finished, lengths)
+        scores, word, parent, log_probs, finished, lengths, margin = beam_step(slp, log_probs, finished, lengths, with_margin=True)
+        s_margin.append(margin)
         flat_parent = (np.arange(B)[:, None] * W + parent).reshape(-1)
         state = state.gather(flat_parent)
         tokens = word.reshape(-1)
@@ -327,9 +345,10 @@ def beam_search(w, enc_output, mask, beam_width, max_output_len, dec_units=128, 
     pred = gather_tree(step_ids, par_ids, lengths.max(axis=1).astype(np.int32))
     pred = np.transpose(pred, (1, 0, 2))
     sc = np.transpose(np.stack(s_scores), (1, 0, 2))
+    extra = (np.stack(s_margin, axis=1),) if return_margins else ()
     if return_all:
-        return pred, sc, np.transpose(step_ids, (1, 0, 2)), np.transpose(par_ids, (1, 0, 2))
-    return pred[:, :, 0], sc[:, :, 0]
+        return (pred, sc, np.transpose(step_ids, (1, 0, 2)), np.transpose(par_ids, (1, 0, 2))) + extra
+    return (pred[:, :, 0], sc[:, :, 0]) + extra
 
 
 def tokens_to_nuc_sequences(tokens):

@@ -40,6 +40,10 @@ constexpr int THREADS = 128 + 32 * EPI_WARPS;    // warpgroup 0: w1 = TMEM alloc
 // Register budget: the launch allocates REG_LAUNCH per thread for all warps; warpgroup 0 then gives most of its share back
 // (setmaxnreg.dec) and the epilogue warpgroups take it (setmaxnreg.inc), so the cell update keeps c, the pre-gate prefetch
 // and a whole 8-unit chunk in registers without spilling.
+#ifndef RVB_REC_PF_CHUNKS
+#define RVB_REC_PF_CHUNKS 2
+#endif
+constexpr int PF_CHUNKS = RVB_REC_PF_CHUNKS;     // pre-gates: L2 prefetch this many chunks beyond the two register buffers (0 = off)
 constexpr int REG_IDLE = 72;
 constexpr int REG_EPI = EPI_WARPS == 8 ? 216 : 120;
 constexpr int ROWS = 128;             // batch rows per CTA
@@ -483,6 +487,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                     const int un = unit_of((i + 2) % NCH);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) gbuf[i & 1][k] = __ldg(nsrc + (size_t)(un + k) * gq);
+                    if (PF_CHUNKS > 0) {
+                        // registers hold two chunks (64 KB in flight per SM is not enough for the DRAM latency): keep PF_CHUNKS more on
+                        // their way into L2.  Measured: 13.2 -> 11.6 us per step; a bulk prefetch of whole steps ADDS DRAM traffic.
+                        const float4 *psrc = (i + 2 + PF_CHUNKS < NCH) ? grow : grow_next;
+                        const int up = unit_of((i + 2 + PF_CHUNKS) % NCH);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(psrc + (size_t)(up + k) * gq));
+                    }
                 };
                 if (PRE && ch != CPQ - 1) refill();
                 if (i + 1 < NCH) {

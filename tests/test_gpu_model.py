@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from oracle import model_ref as mr
+from oracle.parity import check_beam
 
 pytestmark = pytest.mark.gpu
 
@@ -73,13 +74,10 @@ def _first_diff(a, b):
     return int(d[0]) if d.size else None
 
 
-@pytest.mark.parametrize("kind", ["raw", "joint"])
-def test_greedy_matches_oracle(kind):
-    n, L = 96, 20
-    x = inputs(kind, n, seed=6)
-    ids, logits = make(kind).greedy_search_prediction(x, L)
-    enc, mask = mr.encode_input(W22, x, kind)
-    rid, rlog = mr.greedy_search(W22, enc, mask, L)
+def _check_greedy(ids, logits, rid, rlog):
+    """Greedy rows are identical to the oracle's except for near-tie argmax flips: at the first differing step the
+    oracle's top-2 logit margin is < 1e-3; logits agree up to and including that step."""
+    n = len(rid)
     assert ids.shape == rid.shape and ids.dtype == np.int32 and logits.shape == rlog.shape
     flips = 0
     for b in range(n):
@@ -93,17 +91,30 @@ def test_greedy_matches_oracle(kind):
     assert flips <= max(1, n // 50), f"{flips} near-tie flips in {n} rows"
 
 
+@pytest.mark.parametrize("kind", ["raw", "joint"])
+def test_greedy_matches_oracle(kind):
+    n, L = 96, 20
+    x = inputs(kind, n, seed=6)
+    ids, logits = make(kind).greedy_search_prediction(x, L)
+    enc, mask = mr.encode_input(W22, x, kind)
+    rid, rlog = mr.greedy_search(W22, enc, mask, L)
+    _check_greedy(ids, logits, rid, rlog)
+
+
 @pytest.mark.parametrize("kind,W", [("joint", 1), ("joint", 5), ("event", 5), ("raw", 3)])
 def test_beam_matches_oracle(kind, W):
+    """Every row identical to the oracle in every beam slot (ids, parents, gather_tree output, scores), except rows
+    that diverge first at a step where the oracle's own top-(W+1) margin is < 1e-3 (oracle/parity.py)."""
     n, L = 70, 16
     x = inputs(kind, n, seed=8)
-    ids, sc = make(kind).beam_search_prediction(x, W, L)
+    bc = make(kind)
+    got = bc.beam_search_prediction(x, W, L, return_all_beams=True)
     enc, mask = mr.encode_input(W22, x, kind)
-    rid, rsc = mr.beam_search(W22, enc, mask, W, L)
-    assert ids.shape == rid.shape and sc.shape == rsc.shape
-    same = np.array([np.array_equal(ids[b], rid[b]) for b in range(n)])
-    assert same.mean() >= 0.95, f"only {same.mean():.3f} of beam results identical"
-    np.testing.assert_allclose(sc[same], rsc[same], rtol=RTOL, atol=1e-4)
+    ties = check_beam(got, W22, enc, mask, W, L, atol=1e-4, label=f" {kind} W={W}")
+    ids, sc = bc.beam_search_prediction(x, W, L)                 # the reference's return value: beam slot 0
+    assert np.array_equal(ids, got[0][:, :, 0]) and np.array_equal(sc, got[1][:, :, 0])
+    assert ids.dtype == np.int32 and sc.dtype == np.float32
+    assert ties == 0 or ties <= 2
 
 
 @pytest.mark.parametrize("W", [1, 5])
@@ -116,14 +127,11 @@ def test_beam_early_termination_matches_oracle(W):
     w["decoder/fc/bias"] = b
     n, L = 50, 20
     x = inputs("joint", n, seed=11)
-    ids, sc = make("joint", weights=w).beam_search_prediction(x, W, L)
+    got = make("joint", weights=w).beam_search_prediction(x, W, L, return_all_beams=True)
     enc, mask = mr.encode_input(w, x, "joint")
-    rid, rsc = mr.beam_search(w, enc, mask, W, L)
+    rid, _ = mr.beam_search(w, enc, mask, W, L)
     assert rid.shape[1] < L - 1, "the bias should end decoding early"
-    assert ids.shape == rid.shape
-    same = np.array([np.array_equal(ids[i], rid[i]) for i in range(n)])
-    assert same.mean() >= 0.9, same.mean()
-    np.testing.assert_allclose(sc[same], rsc[same], rtol=1e-3, atol=2e-4)
+    check_beam(got, w, enc, mask, W, L, label=f" early-stop W={W}")
 
 
 @pytest.mark.parametrize("enc_depth,W", [(3, 1), (3, 5), (2, 5)])
@@ -135,19 +143,12 @@ def test_decoder_depth_2(enc_depth, W):
     x = inputs("joint", n, seed=12)
     bc = make("joint", depth=enc_depth, weights=w, dec_depth=2)
     enc, mask = mr.encode_input(w, x, "joint", encoder_depth=enc_depth)
-    ids, sc = bc.beam_search_prediction(x, W, L)
-    rid, rsc = mr.beam_search(w, enc, mask, W, L, decoder_depth=2)
-    assert ids.shape == rid.shape
-    same = np.array([np.array_equal(ids[i], rid[i]) for i in range(n)])
-    assert same.mean() >= 0.9, same.mean()
-    np.testing.assert_allclose(sc[same], rsc[same], rtol=1e-3, atol=2e-4)
+    got = bc.beam_search_prediction(x, W, L, return_all_beams=True)
+    check_beam(got, w, enc, mask, W, L, decoder_depth=2, label=f" depth ({enc_depth},2) W={W}")
     if W == 1:
         gid, glog = bc.greedy_search_prediction(x, L)
         rgid, rglog = mr.greedy_search(w, enc, mask, L, decoder_depth=2)
-        assert gid.shape == rgid.shape
-        ok = np.array([np.array_equal(gid[i], rgid[i]) for i in range(n)])
-        assert ok.mean() >= 0.9
-        np.testing.assert_allclose(glog[ok], rglog[ok], rtol=1e-3, atol=2e-4)
+        _check_greedy(gid, glog, rgid, rglog)
 
 
 def test_beam_all_beams_internal_consistency():
@@ -287,11 +288,7 @@ def test_beam_width_and_batch_edges(W, n):
     raw, ev = mr.synth_chunks(np.random.default_rng(21 + W), n)
     raw[0, 17, 0] = 0.0                                   # interior row masked out (utils.input_mask: any zero feature)
     ev[n - 1, 3, :] = 0.0
-    ids, sc = make("joint").beam_search_prediction((raw, ev), W, L)
+    got = make("joint").beam_search_prediction((raw, ev), W, L, return_all_beams=True)
     enc, mask = mr.encode_input(W22, (raw, ev), "joint")
     assert not mask[0, 17] and not mask[n - 1, 200 + 3]
-    rid, rsc = mr.beam_search(W22, enc, mask, W, L)
-    assert ids.shape == rid.shape
-    same = np.array([np.array_equal(ids[b], rid[b]) for b in range(n)])
-    assert same.mean() >= 0.8, (same, ids, rid)
-    np.testing.assert_allclose(sc[same], rsc[same], rtol=RTOL, atol=1e-4)
+    check_beam(got, W22, enc, mask, W, L, atol=1e-4, label=f" edges W={W} n={n}")

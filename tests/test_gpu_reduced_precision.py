@@ -43,12 +43,12 @@ def test_search_within_stated_tolerance(W):
     x = mr.synth_chunks(np.random.default_rng(2), 96)
     bc = make("joint")
     enc, mask = mr.encode_input(W22, x, "joint")
-    ids, sc = bc.beam_search_prediction(x, W, 20)
-    rid, rsc = mr.beam_search(W22, enc, mask, W, 20)
-    assert ids.shape == rid.shape
-    same = np.array([np.array_equal(a, b) for a, b in zip(ids, rid)])
-    assert same.mean() >= MIN_IDENTICAL, same.mean()
-    assert np.abs(sc[same] - rsc[same]).max() < SCORE_ATOL
+    from oracle.parity import check_beam
+    got = bc.beam_search_prediction(x, W, 20, return_all_beams=True)
+    # rows may leave the fp32 oracle only where its own top-(W+1) margin is within the stated score tolerance, and at
+    # most 1 - MIN_IDENTICAL of them; all other rows are identical in every beam slot, scores within SCORE_ATOL
+    check_beam(got, W22, enc, mask, W, 20, tie_eps=2 * SCORE_ATOL, max_tie_frac=1 - MIN_IDENTICAL, rtol=0, atol=SCORE_ATOL,
+               label=f" reduced precision W={W}")
     if W == 1:
         gid, glog = bc.greedy_search_prediction(x, 20)
         rgid, rglog = mr.greedy_search(W22, enc, mask, 20)

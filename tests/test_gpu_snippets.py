@@ -42,11 +42,11 @@ def test_against_oracle_on_a_full_read_and_feeds_the_event_model():
     w = mr.init_weights(22)
     bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, 'event', 0.)
     bc.load_weights(w)
-    ids, sc = bc.beam_search_prediction(es[:64], 1, 12)
-    enc, mask = mr.encode_input(w, ref["event"][:64], "event")
-    rid, rsc = mr.beam_search(w, enc, mask, 1, 12)
-    same = np.array([np.array_equal(a, b) for a, b in zip(ids.cpu().numpy(), rid)])
-    assert same.mean() >= 0.95
+    from oracle.parity import check_beam
+    got = bc.beam_search_prediction(es[:64], 1, 12, return_all_beams=True)
+    # the GPU snippets may differ from the oracle's by 1 ulp (see _ulp_close): feed the oracle the GPU's own snippets
+    enc, mask = mr.encode_input(w, es[:64].cpu().numpy(), "event")
+    check_beam([g.cpu().numpy() for g in got], w, enc, mask, 1, 12, label=" event model on GPU-built snippets")
 
 
 def test_short_and_empty_reads():
