@@ -2,21 +2,31 @@
 """bench.py -- throughput of the Ravvent inference hot path on B200 (contract: see DESIGN.md §6).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--chunks C] [--beam 1|5] [--precision fp32|bf16]
+                  [--chunks C] [--beam 1|5] [--precision fp32|bf16] [--single-process]
 
-A "step" is one pass of the hot path (encoders -> attention decoder -> beam search)
-over one batch of C synthetic joint chunks (raw [C,200,1] + event [C,30,5]) per GPU.
-Workload at N=1: BASELINE.json configs[2] "joint raw+event model, beam1, 100k synthetic
-chunks on 1 B200"; the beam-5 figure of configs[3] is measured in the same run and
-reported under "beam5".  Weak scaling: every rank processes its own C chunks
-(read-sharded, no collective on the data path).
+A "step" is one pass of the hot path (encoders -> attention decoder -> beam search) over one batch of
+synthetic joint chunks (raw [C,200,1] + event [C,30,5]).
 
-metric  = read-equivalent bases/s = chunks/s x 6.4 (stride-6 windows advance ~6.4 bases
-          per chunk on the synthetic generator) -- identical definition for
-          the CUDA path and the CPU reference arm.
+N = 1   BASELINE.json configs[2]: joint model, beam 1, 100k chunks on one B200 (`value`, `e2e`, `roofline`,
+        `kernels`), plus in the same line: `beam5` (configs[3], with its own `kernels` / `roofline`),
+        `raw_greedy_1k` (configs[0]), `event_only` (configs[1]: reads -> GPU event detection -> snippet
+        builder -> event model, beam 1), `depth_3_2` (the reference's best-accuracy configuration),
+        `event_path`, `read_path`, `cpu_baseline`.
+N > 1   (torchrun, one rank per GPU) BASELINE.json configs[4]: ONE fixed batch of --sweep-chunks (1M) joint
+        chunks, read-sharded into contiguous ranges (strong scaling).  `value`: device-resident shards,
+        max over ranks.  `e2e`: every rank copies its shard in from pageable host memory, decodes it and
+        writes its rows at their input positions of one host array shared by the ranks (/dev/shm) -- the
+        scatter and the ordered host-side gather are inside the timed region.  `weak_100k_per_gpu` keeps the
+        round-1 figure (every rank its own 100k chunks).  NCCL carries only the contract's barrier and the
+        max-over-ranks of the timing; there is no collective on the data path.
+--single-process   the same 1M sweep through ShardedBasecaller (one process, one host thread + handle +
+        staging ring per GPU) instead of torchrun ranks.
+
+metric  = read-equivalent bases/s = chunks/s x 6.4 (stride-6 windows advance ~6.4 bases per chunk on the
+          synthetic generator) -- identical definition for the CUDA path and the CPU arm.
 value   = device-resident inputs, CUDA-event timed, max over ranks.
-e2e     = same metric through Basecaller.beam_search_prediction with HOST numpy buffers
-          (pinned), H2D + D2H inside the timed region.
+e2e     = same metric through Basecaller.beam_search_prediction with plain (pageable) numpy buffers,
+          H2D + D2H inside the timed region.
 """
 from __future__ import annotations
 
@@ -58,6 +68,26 @@ def synth_chunks(rng, n):
     el = rng.integers(16, 28, size=n)
     ev[np.arange(T_EV)[None, :] >= el[:, None]] = 0.0
     return raw, ev
+
+
+GEN_BLOCK = 10000
+
+
+def synth_range(lo, hi, seed=1234):
+    """Chunks [lo, hi) of the one synthetic chunk set (independent of how it is sharded): block i of GEN_BLOCK chunks
+    comes from default_rng(seed + i)."""
+    raws, evs = [], []
+    for blk in range(lo // GEN_BLOCK, (max(hi, lo + 1) - 1) // GEN_BLOCK + 1):
+        r, e = synth_chunks(np.random.default_rng(seed + blk), GEN_BLOCK)
+        a, b = max(lo, blk * GEN_BLOCK) - blk * GEN_BLOCK, min(hi, (blk + 1) * GEN_BLOCK) - blk * GEN_BLOCK
+        raws.append(r[a:b]); evs.append(e[a:b])
+    return np.concatenate(raws), np.concatenate(evs)
+
+
+def shard_range(n, rank, world):
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
 
 
 class ClockSampler:
@@ -129,17 +159,19 @@ def measured_peaks():
 # reference arm / cpu_baseline: the oracle port of the TF path on the host cores
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_rate(n_chunks, beam, repeats=1):
-    import torch
+    from threadpoolctl import threadpool_limits
     from oracle import model_ref as mr
     w = mr.init_weights(22)
-    raw, ev = synth_chunks(np.random.default_rng(1234), n_chunks)
-    t0 = time.perf_counter()
-    for _ in range(repeats):
-        for b0 in range(0, n_chunks, 1024):       # reference predict batch (ravvent_performance_evaluator.py:24)
-            enc, mask = mr.encode_input(w, (raw[b0:b0 + 1024], ev[b0:b0 + 1024]), "joint")
-            mr.beam_search(w, enc, mask, beam, MAX_OUTPUT_LEN, full_length=True)
-    dt = (time.perf_counter() - t0) / repeats
-    return n_chunks / dt * BASES_PER_CHUNK, dt, torch.get_num_threads()
+    raw, ev = synth_range(0, n_chunks)
+    cores = os.cpu_count() or 1
+    with threadpool_limits(limits=cores):         # torchrun exports OMP_NUM_THREADS=1: give the BLAS its cores back
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            for b0 in range(0, n_chunks, 1024):       # reference predict batch (ravvent_performance_evaluator.py:24)
+                enc, mask = mr.encode_input(w, (raw[b0:b0 + 1024], ev[b0:b0 + 1024]), "joint")
+                mr.beam_search(w, enc, mask, beam, MAX_OUTPUT_LEN, full_length=True)
+        dt = (time.perf_counter() - t0) / repeats
+    return n_chunks / dt * BASES_PER_CHUNK, dt, cores
 
 
 def run_reference(args, rank, world):
@@ -171,60 +203,42 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------------------------
 # CUDA arm
 # ----------------------------------------------------------------------------------------------
-def run_ours(args, rank, local_rank, world):
-    import torch
-    import ravvent_basecaller_b200 as rb
-    from ravvent_basecaller_b200 import _lib
+class Timer:
+    """The contract's timing: W untimed warm-up steps, then exactly K steps between barrier + synchronize, CUDA events,
+    max over ranks; L2 flushed between timed iterations."""
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, dev, local_rank, dist):
+        import torch
+        self.torch, self.dev, self.local_rank, self.dist = torch, dev, local_rank, dist
+        self.l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
 
-    def max_over_ranks(x):
-        if dist is None:
+    def max_over_ranks(self, x):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    C = args.chunks
-    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "joint", 0., encoder_depth=2, decoder_depth=1, device=local_rank,
-                       precision=args.precision)
-    bc.compile(optimizer=None)
-    bc.load_weights(seed=22)
-    raw_h, ev_h = synth_chunks(np.random.default_rng(1234 + rank), C)
-    raw_p = torch.from_numpy(raw_h).pin_memory(); ev_p = torch.from_numpy(ev_h).pin_memory()
-    raw_d = raw_p.to(dev); ev_d = ev_p.to(dev)
-    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step_device(beam):
-        ids, sc = bc.beam_search_prediction((raw_d, ev_d), beam, MAX_OUTPUT_LEN)
-        return ids
-
-    def step_host(beam):
-        ids, sc = bc.beam_search_prediction((raw_p.numpy(), ev_p.numpy()), beam, MAX_OUTPUT_LEN)
-        return ids
-
-    def timed(fn, beam, steps, warmup, sample_clocks=False, profile=False):
+    def run(self, fn, steps, warmup, sample_clocks=False, profile=False):
+        """-> dict(ms per step (max over ranks), launches, clocks, last result, per-kernel profile, per-step ms)."""
+        torch = self.torch
+        from ravvent_basecaller_b200 import _lib
         held = []                           # keep two generations of outputs alive so the caching allocator owns both
         for _ in range(max(warmup, 2)):     # buffer sets before the timed region (the timed loop holds one while making the next)
-            held.append(fn(beam))
+            held.append(fn())
             held = held[-2:]
         del held
-        sampler = ClockSampler(local_rank) if (sample_clocks and not os.environ.get('BENCH_NO_CLOCKS')) else None
-        barrier()
+        sampler = ClockSampler(self.local_rank) if (sample_clocks and not os.environ.get('BENCH_NO_CLOCKS')) else None
+        self.barrier()
         if sampler:
             sampler.start(); time.sleep(0.3)
-        keep = fn(beam)                     # one more untimed step: the GPU idled during the set-up above (clock ramp)
-        barrier()
+        keep = fn()                         # one more untimed step: the GPU idled during the set-up above (clock ramp)
+        self.barrier()
         del keep
         n0 = _lib.launch_count()
         t0w = time.time()
@@ -232,15 +246,14 @@ def run_ours(args, rank, local_rank, world):
         if profile:
             _lib.profile(True)
         ev0.record()
-        ids = None
-        marks = []
+        out, marks = None, []
         for _ in range(steps):
             if not os.environ.get('BENCH_NO_FLUSH'):
-                l2_flush.zero_()           # inputs (97 MB) < L2 (126 MB): flush between timed iterations
-            ids = fn(beam)
+                self.l2_flush.zero_()       # flush L2 between timed iterations
+            out = fn()
             m = torch.cuda.Event(enable_timing=True); m.record(); marks.append(m)
         ev1.record()
-        barrier()
+        self.barrier()
         t1w = time.time()
         ms = ev0.elapsed_time(ev1)
         launches = _lib.launch_count() - n0
@@ -252,75 +265,305 @@ def run_ours(args, rank, local_rank, world):
         prev, per_step = ev0, []
         for m in marks:
             per_step.append(round(prev.elapsed_time(m), 2)); prev = m
-        timed.last_per_step = per_step
-        return max_over_ranks(ms) / steps, launches, clocks, ids, prof
+        return {"ms": self.max_over_ranks(ms) / steps, "launches": launches, "clocks": clocks, "out": out, "prof": prof,
+                "per_step": per_step}
 
-    ms1, launches, clocks, ids1, prof = timed(step_device, args.beam, args.steps, args.warmup, sample_clocks=True, profile=True)
-    per_step_ms = list(timed.last_per_step)
+
+def roofline_entry(kr, ms_step, steps, peak, peak_src, precision, valid_rows):
+    dom = max(kr, key=lambda k: kr[k]["ms"])
+    return {"bound": "hbm", "achieved": kr[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kr[dom]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dom) if precision == "fp32" else None, "peak_source": peak_src,
+            "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms_step * steps),
+            "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
+            "achieved_tflops": kr[dom]["tflops"], "valid_memory_rows_per_chunk": valid_rows,
+            "note": "achieved = algorithmic bytes (DESIGN.md 4.5-4.6: memory rows admitted by the mask x 1 KB per snippet "
+                    "and decode step) / CUDA-event time of the kernel's launches in the timed region; peak = measured "
+                    "copy bandwidth (a read-only stream can slightly exceed it); traffic = dram bytes of ONE launch on a "
+                    "9472-chunk wave from the committed ncu capture (profiles/), launches here cover up to 9472 chunks each"}
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import ravvent_basecaller_b200 as rb
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)      # barrier + max of the timing only
+    tm = Timer(dev, local_rank, dist)
+    strong = world > 1
+    total = args.sweep_chunks if strong else args.chunks
+    lo, hi = shard_range(total, rank, world)
+    C = hi - lo
+    S = MAX_OUTPUT_LEN - 1
+
+    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "joint", 0., encoder_depth=2, decoder_depth=1, device=local_rank,
+                       precision=args.precision)
+    bc.compile(optimizer=None)
+    bc.load_weights(seed=22)
+    raw_h, ev_h = synth_range(lo, hi)                       # plain (pageable) numpy: what a reference caller holds
+    raw_d = torch.from_numpy(raw_h).to(dev); ev_d = torch.from_numpy(ev_h).to(dev)
+
+    # host-side gather target of the sharded e2e run: one [total, S] array pair shared by the ranks
+    shm = None
+    if strong:
+        base = "/dev/shm/rvb_bench_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            np.lib.format.open_memmap(base + "_ids.npy", mode="w+", dtype=np.int32, shape=(total, S)).flush()
+            np.lib.format.open_memmap(base + "_sc.npy", mode="w+", dtype=np.float32, shape=(total, S)).flush()
+        tm.barrier()
+        shm = (np.load(base + "_ids.npy", mmap_mode="r+"), np.load(base + "_sc.npy", mmap_mode="r+"))
+
+    def step_device(beam):
+        return bc.beam_search_prediction((raw_d, ev_d), beam, MAX_OUTPUT_LEN)[0]
+
+    def step_host(beam):
+        ids, sc = bc.beam_search_prediction((raw_h, ev_h), beam, MAX_OUTPUT_LEN)
+        if shm is not None:                                 # ordered gather: this rank's rows at their input positions
+            T = ids.shape[1]
+            shm[0][lo:hi, :T] = ids
+            shm[1][lo:hi, :T] = sc
+        return ids
+
+    r1 = tm.run(lambda: step_device(args.beam), args.steps, args.warmup, sample_clocks=True, profile=True)
     other = 5 if args.beam == 1 else 1
-    ms_o, _, _, _, _ = timed(step_device, other, max(1, args.steps // 2), 1)
-    ms_e2e, _, _, _, _ = timed(step_host, args.beam, max(1, args.steps // 2), 1)
+    ro = tm.run(lambda: step_device(other), max(1, args.steps // 2), 1, profile=True)
+    re = tm.run(lambda: step_host(args.beam), max(1, args.steps // 2), 1)
+    ms1, ms_o, ms_e2e = r1["ms"], ro["ms"], re["ms"]
+    gathered_ok = None
+    if strong:
+        tm.barrier()
+        if rank == 0:                                       # every shard landed where its inputs were
+            probe = np.linspace(0, total - 1, 64).astype(np.int64)
+            gathered_ok = bool((shm[0][probe, 0] >= 1).all() and (shm[0][probe, 0] <= 6).all())
 
-    chunks_total = C * world
-    rate = lambda ms: chunks_total / (ms * 1e-3)
+    weak = None
+    if strong and not args.no_weak:
+        # round-1 figure: every rank its own 100k chunks (weak scaling of replicas)
+        n_w = 100000
+        rw, ew = synth_range(rank * n_w, (rank + 1) * n_w, seed=99000)
+        rw_d, ew_d = torch.from_numpy(rw).to(dev), torch.from_numpy(ew).to(dev)
+        rwk = tm.run(lambda: bc.beam_search_prediction((rw_d, ew_d), args.beam, MAX_OUTPUT_LEN)[0], max(1, args.steps // 2), 1)
+        weak = {"value": n_w * world / (rwk["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": rwk["ms"],
+                "chunks_per_gpu": n_w, "scaling": "weak"}
+        del rw_d, ew_d
+
+    rate = lambda ms: total / (ms * 1e-3) if strong else C * world / (ms * 1e-3)
+    ids1 = r1["out"]
     ids_np = ids1.cpu().numpy() if hasattr(ids1, "cpu") else np.asarray(ids1)
     is_end = ids_np == 1
     first_end = np.where(is_end.any(axis=1), is_end.argmax(axis=1), ids_np.shape[1])
     called = int((((ids_np >= 3) & (ids_np <= 6)) & (np.arange(ids_np.shape[1])[None, :] < first_end[:, None])).sum())
 
-    # ---- roofline of the dominant kernel (K3, persistent recurrent LSTM), timed live with CUDA events
+    # ---- per-kernel rooflines, timed live with the library's CUDA events on the launching stream
     peak, peak_src = measured_peaks()
     # memory rows the input mask admits (masked rows contribute nothing to the softmax and are not read)
-    valid_rows = float(((raw_d != 0).all(dim=-1).sum() + (ev_d != 0).all(dim=-1).sum()).item()) / C
-    kr = kernel_rooflines(prof, args.steps, C, args.beam, peak, args.precision, valid_rows)
-    dom = max(kr, key=lambda k: kr[k]["ms"])
+    valid_rows = float(((raw_d != 0).all(dim=-1).sum() + (ev_d != 0).all(dim=-1).sum()).item()) / max(C, 1)
+    kr = kernel_rooflines(r1["prof"], args.steps, C, args.beam, peak, args.precision, valid_rows)
+    kro = kernel_rooflines(ro["prof"], max(1, args.steps // 2), C, other, peak, args.precision, valid_rows)
 
-    line = None
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_configs:
+        del raw_d, ev_d
+        extras = other_configs(args, local_rank, tm)
     if rank == 0:
-        S = MAX_OUTPUT_LEN - 1
         h2d = C * (T_RAW + T_EV * 5) * 4
         d2h = C * S * 8 + 4
         cpu = None
         if not args.no_cpu_baseline and world == 1:          # rank 0 at N=1 only (contract)
             v, dt, thr = cpu_reference_rate(args.ref_chunks, args.beam)
-            cpu = {"value": v, "unit": "bases/s", "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": v, "unit": "bases/s", "cores": thr, "kind": "port",
                    "sample": "%d joint chunks, beam%d, numpy/BLAS restatement of the TF path (oracle/model_ref.py), "
                              "%.1f s" % (args.ref_chunks, args.beam, dt)}
+        workload = ("joint raw+event model (enc 2x BiLSTM-128, dec LSTM-128 + Luong), beam%d, S=33 decode steps, " % args.beam) + (
+            "ONE fixed batch of %d synthetic chunks read-sharded over %d GPUs (BASELINE configs[4])" % (total, world) if strong
+            else "%d synthetic chunks on one GPU (BASELINE configs[2])" % C)
         line = {
             "metric": "read-equivalent bases/sec (joint model, beam%d)" % args.beam,
             "value": rate(ms1) * BASES_PER_CHUNK, "unit": "bases/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms1, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms1, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": "joint raw+event model (enc 2x BiLSTM-128, dec LSTM-128 + Luong), beam%d, "
-                                   "S=33 decode steps, %d synthetic chunks per GPU" % (args.beam, C),
-                       "chunks_per_gpu": C, "max_output_len": MAX_OUTPUT_LEN, "weights": "Keras-default init, seed 22",
-                       "l2": "256 MiB buffer written between timed iterations", "parallelism": "read-sharded x%d, no collective" % world},
-            "chunks_per_s": rate(ms1), "called_bases_per_s": called * world / (ms1 * 1e-3),
+            "config": {"workload": workload, "chunks_total": total if strong else C * world, "chunks_per_gpu": C,
+                       "max_output_len": MAX_OUTPUT_LEN, "weights": "Keras-default init, seed 22",
+                       "l2": "256 MiB buffer written between timed iterations",
+                       "parallelism": ("contiguous read shards x%d, one process per GPU, no data-path collective; NCCL carries only the "
+                                       "barrier and the max-over-ranks of the timing; e2e gathers the shards in input order into one "
+                                       "host array (/dev/shm)" % world) if strong else "single GPU"},
+            "chunks_per_s": rate(ms1), "called_bases_per_s": called * (1 if strong else world) / (ms1 * 1e-3),
             "tflops_algorithmic": rate(ms1) * FLOP_PER_CHUNK[args.beam] / 1e12,
             "beam%d" % other: {"value": rate(ms_o) * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": ms_o,
-                               "chunks_per_s": rate(ms_o)},
+                               "chunks_per_s": rate(ms_o), "kernels": kro,
+                               "roofline": roofline_entry(kro, ms_o, max(1, args.steps // 2), peak, peak_src, args.precision, valid_rows)},
             "e2e": {"value": rate(ms_e2e) * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": kr[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": kr[dom]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dom) if args.precision == "fp32" else None, "peak_source": peak_src,
-                         "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms1 * args.steps),
-                         "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
-                         "achieved_tflops": kr[dom]["tflops"],
-                         "valid_memory_rows_per_chunk": valid_rows,
-                         "note": "achieved = algorithmic bytes (DESIGN.md 4.5-4.6: memory rows admitted by the mask x 1 KB per snippet "
-                                 "and decode step) / CUDA-event time of the kernel's launches in the timed region; peak = measured "
-                                 "copy bandwidth (a read-only stream can slightly exceed it); traffic = dram bytes of ONE launch on a "
-                                 "9472-chunk wave from the committed ncu capture (profiles/), launches here cover up to 9472 chunks each"},
-            "kernels": kr, "step_ms": per_step_ms,
-            "event_path": event_path_bench(local_rank) if (not args.no_event_path and world == 1) else None,
-            "read_path": read_path_bench(local_rank, args.beam, args.precision) if (not args.no_event_path and world == 1) else None,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_buffers": "pageable numpy (staged through the handle's pinned ring)",
+                    "gathered_in_input_order": gathered_ok},
+            "gpu_launches": r1["launches"], "clocks": r1["clocks"],
+            "roofline": roofline_entry(kr, ms1, args.steps, peak, peak_src, args.precision, valid_rows),
+            "kernels": kr, "step_ms": r1["per_step"],
         }
+        if weak:
+            line["weak_100k_per_gpu"] = weak
+        line.update(extras)
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+    if strong:
+        tm.barrier()
+        del shm
+        if rank == 0:
+            for suf in ("_ids.npy", "_sc.npy"):
+                try:
+                    os.unlink("/dev/shm/rvb_bench_%s%s" % (os.environ.get("MASTER_PORT", "0"), suf))
+                except OSError:
+                    pass
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_single_process(args):
+    """BASELINE configs[4] through the product's own multi-GPU call: ShardedBasecaller.beam_search_prediction on ONE host
+    batch (pageable numpy) -- one handle, host thread, stream set and pinned staging ring per GPU, results written in input
+    order into one host array.  Host wall clock around the call (H2D, compute, D2H, gather all inside)."""
+    import torch
+    import ravvent_basecaller_b200 as rb
+    n_dev = min(args.gpus, torch.cuda.device_count())
+    total = args.sweep_chunks
+    sb = rb.ShardedBasecaller(128, 128, 128, rb.nuc_tk, "joint", 0., devices=list(range(n_dev)), precision=args.precision)
+    sb.load_weights(seed=22)
+    raw_h, ev_h = synth_range(0, total)
+    res = {}
+    for beam in (args.beam, 5 if args.beam == 1 else 1):
+        for _ in range(max(1, min(args.warmup, 2))):
+            sb.beam_search_prediction((raw_h, ev_h), beam, MAX_OUTPUT_LEN)
+        ts = []
+        for _ in range(max(1, args.steps)):
+            for d in range(n_dev):
+                torch.cuda.synchronize(d)
+            t0 = time.perf_counter()
+            ids, sc = sb.beam_search_prediction((raw_h, ev_h), beam, MAX_OUTPUT_LEN)
+            ts.append(time.perf_counter() - t0)
+        res[beam] = float(np.mean(ts))
+    dt = res[args.beam]
+    S = MAX_OUTPUT_LEN - 1
+    line = {"metric": "read-equivalent bases/sec (joint model, beam%d)" % args.beam, "value": total / dt * BASES_PER_CHUNK,
+            "unit": "bases/s", "n_gpus": n_dev, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "joint raw+event model, beam%d, S=33, ONE fixed batch of %d synthetic chunks (BASELINE configs[4])"
+                                   % (args.beam, total),
+                       "parallelism": "single process: ShardedBasecaller, one host thread + handle + pinned staging ring per GPU, "
+                                      "contiguous shards, results written in input order into one host array; no NCCL"},
+            "e2e": {"value": total / dt * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": dt * 1e3,
+                    "h2d_bytes_per_step": total * (T_RAW + T_EV * 5) * 4, "d2h_bytes_per_step": total * S * 8,
+                    "host_buffers": "pageable numpy", "timing": "host wall clock around the call (it returns host arrays)"},
+            "beam%d" % (5 if args.beam == 1 else 1): {"value": total / res[5 if args.beam == 1 else 1] * BASES_PER_CHUNK,
+                                                      "ms_per_step": res[5 if args.beam == 1 else 1] * 1e3},
+            "gpu_launches": int(rb.launch_count())}
+    print(json.dumps(line), flush=True)
+
+
+def other_configs(args, local_rank, tm):
+    """The BASELINE.json configs that are not the headline, each timed like the headline (N = 1 only)."""
+    import torch
+    import ravvent_basecaller_b200 as rb
+    dev = torch.device("cuda", local_rank)
+    out = {}
+    k = max(2, args.steps // 2)
+    # configs[0]: raw-only model, greedy (beam 1), 1k chunks -- Basecaller.greedy_search_prediction
+    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "raw", 0., device=local_rank, precision=args.precision).load_weights(seed=22)
+    raw_h = synth_range(0, 1000)[0]
+    raw_d = torch.from_numpy(raw_h).to(dev)
+    a = tm.run(lambda: bc.greedy_search_prediction(raw_d, MAX_OUTPUT_LEN)[0], 4 * k, 2)
+    b = tm.run(lambda: bc.greedy_search_prediction(raw_h, MAX_OUTPUT_LEN)[0], 4 * k, 2)
+    out["raw_greedy_1k"] = {"config": "BASELINE configs[0]: raw-only model, greedy search, 1000 chunks, S=33", "ms_per_step": a["ms"],
+                            "value": 1000 / (a["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s",
+                            "e2e": {"value": 1000 / (b["ms"] * 1e-3) * BASES_PER_CHUNK, "ms_per_step": b["ms"]},
+                            "launches_per_step": a["launches"] // (4 * k),
+                            "note": "one partial wave (1000 of 9472 rows): latency of 2 x 200 recurrent timesteps + 33 decode steps, not throughput"}
+    big = synth_range(0, 100000)[0]
+    big_d = torch.from_numpy(big).to(dev)
+    a = tm.run(lambda: bc.greedy_search_prediction(big_d, MAX_OUTPUT_LEN)[0], k, 1)
+    out["raw_greedy_100k"] = {"ms_per_step": a["ms"], "value": 100000 / (a["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s"}
+    del bc, raw_d, big_d, big
+    # configs[1]: event-only model fed by GPU event detection
+    out["event_only"] = event_only_bench(args, local_rank, tm)
+    # the reference's best-accuracy configuration: encoder depth 3, decoder depth 2 (accuracy_results_all.lambda.beam5.json)
+    n32 = 30000
+    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "joint", 0., encoder_depth=3, decoder_depth=2, device=local_rank,
+                       precision=args.precision).load_weights(seed=22)
+    rh, eh = synth_range(0, n32)
+    rd, ed = torch.from_numpy(rh).to(dev), torch.from_numpy(eh).to(dev)
+    d32 = {"config": "joint model, encoder_depth 3, decoder_depth 2, %d chunks, S=33" % n32}
+    for beam in (1, 5):
+        a = tm.run(lambda: bc.beam_search_prediction((rd, ed), beam, MAX_OUTPUT_LEN)[0], k, 1)
+        d32["beam%d" % beam] = {"ms_per_step": a["ms"], "value": n32 / (a["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s"}
+    out["depth_3_2"] = d32
+    del bc, rd, ed
+    if not args.no_event_path:
+        out["event_path"] = event_path_bench(local_rank)
+        out["read_path"] = read_path_bench(local_rank, args.beam, args.precision)
+    return out
+
+
+def synth_reads(n_reads, read_len, seed=77, distinct=8):
+    rng = np.random.default_rng(seed)
+    one = []
+    for _ in range(distinct):          # a few distinct reads tiled to n_reads (generation is the slow part on the host)
+        n_lvl = read_len // 3 + 8
+        dwell = 2 + rng.geometric(1.0 / 7.0, size=n_lvl)
+        level = rng.uniform(250.0, 550.0, size=n_lvl)
+        sig = np.repeat(level, dwell)[:read_len] + rng.normal(0.0, 8.0, size=read_len)
+        one.append(np.rint(sig).astype(np.int32))
+    return one, np.concatenate([one[i % distinct] for i in range(n_reads)])
+
+
+def event_only_bench(args, local_rank, tm, n_reads=96, read_len=60000):
+    """BASELINE configs[1] as ONE timed pipeline: raw reads on the device -> K1 event scan (all reads in one launch) ->
+    snippet builder (per read) -> event encoder + attention decoder + beam 1.  96 reads x 60 000 samples ~ 100k snippets."""
+    import ctypes as C
+    import torch
+    import ravvent_basecaller_b200 as rb
+    from ravvent_basecaller_b200 import _lib
+    from ravvent_basecaller_b200 import data_loader as dl
+    dev = torch.device("cuda", local_rank)
+    _, sig = synth_reads(n_reads, read_len)
+    offs = np.arange(n_reads + 1, dtype=np.int64) * read_len
+    d_sig = torch.from_numpy(sig).to(dev)
+    det = rb.EventDetector(6, 9, device=local_rank)
+    bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "event", 0., device=local_rank, precision=args.precision).load_weights(seed=22)
+    cap_total = n_reads * (read_len // 40)
+    ev_all = torch.zeros((cap_total, dl.MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
+    raw_scratch = torch.zeros((read_len // 40, dl.MAX_RAW_LEN, 1), dtype=torch.float32, device=dev)
+    state = {}
+
+    def pipeline():
+        ev = det.detect_batch(d_sig, offs)
+        counts = ev["count"].cpu().numpy()
+        n = 0
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        for r in range(n_reads):
+            e0 = int(ev["event_offsets"][r])
+            cnt = C.c_int32(0)
+            st, ln, mu, sd = (ev[k][e0:e0 + int(counts[r])] for k in ("start", "length", "mean", "stdv"))
+            cap = max(1, (int(counts[r]) + 5) // 6)
+            _lib.check(_lib.lib.rvb_build_snippets(
+                d_sig[offs[r]:offs[r + 1]].data_ptr(), 4, read_len, st.data_ptr(), ln.data_ptr(), mu.data_ptr(), sd.data_ptr(),
+                int(counts[r]), 0, read_len, 6, raw_scratch.data_ptr(), ev_all[n:].data_ptr(), cap, C.byref(cnt), None, stream))
+            n += cnt.value
+        state["n"] = n
+        return bc.beam_search_prediction(ev_all[:n], 1, MAX_OUTPUT_LEN)[0]
+
+    k = max(2, args.steps // 2)
+    res = tm.run(pipeline, k, 1, profile=True)
+    n = state["n"]
+    return {"config": "BASELINE configs[1]: event-only model fed by GPU event detection, beam 1, S=33", "reads": n_reads,
+            "samples": int(n_reads * read_len), "snippets": n, "ms_per_step": res["ms"],
+            "value": n / (res["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s", "samples_per_s": n_reads * read_len / (res["ms"] * 1e-3),
+            "kernel_ms_per_step": {kk: round(v["ms"] / k, 3) for kk, v in res["prof"].items() if v["ms"] > 0},
+            "note": "wall = event scan (one launch for all reads) + per-read snippet-builder calls (a host sync each: the count comes "
+                    "back to size the next call) + event model; the model itself is the kernel_ms figures"}
 
 
 def kernel_rooflines(prof, steps, chunks, beam, peak_hbm, precision="fp32", valid_rows=float(T_RAW + T_EV)):
@@ -416,15 +659,7 @@ def event_path_bench(local_rank, n_reads=256, read_len=60000, iters=5):
     import torch
     import ravvent_basecaller_b200 as rb
     from ravvent_basecaller_b200 import _lib
-    rng = np.random.default_rng(77)
-    one = []
-    for _ in range(8):          # 8 distinct reads tiled to n_reads (generation is the slow part on the host)
-        n_lvl = read_len // 3 + 8
-        dwell = 2 + rng.geometric(1.0 / 7.0, size=n_lvl)
-        level = rng.uniform(250.0, 550.0, size=n_lvl)
-        sig = np.repeat(level, dwell)[:read_len] + rng.normal(0.0, 8.0, size=read_len)
-        one.append(np.rint(sig).astype(np.int32))
-    sig = np.concatenate([one[i % 8] for i in range(n_reads)])
+    one, sig = synth_reads(n_reads, read_len)
     offs = np.arange(n_reads + 1, dtype=np.int64) * read_len
     dev = torch.device("cuda", local_rank)
     det = rb.EventDetector(6, 9, device=local_rank)
@@ -442,7 +677,8 @@ def event_path_bench(local_rank, n_reads=256, read_len=60000, iters=5):
     res = {"reads": n_reads, "samples": samples, "events": n_events, "ms_per_launch": ms,
            "samples_per_s": samples / (ms * 1e-3), "gbs": bytes_alg / (ms * 1e-3) / 1e9,
            "frac_hbm": bytes_alg / (ms * 1e-3) / 1e9 / peak,
-           "note": "bit-exact float64 t-statistics make this kernel FP64-ALU bound, not HBM bound"}
+           "note": "latency / barrier bound (ncu: FP64 pipe ~6 %, the rest is block-barrier time between the serial phases of a chunk), "
+                   "not HBM bound; < 0.3 % of the pipeline time"}
     # snippet builder on one read (per-read API), wall-clock incl. its stream sync
     raw0 = one[0]
     rb.data_loader.load_data_from_signal(raw0, stride=6, detector=det)
@@ -484,13 +720,20 @@ def main():
     ap.add_argument("--ref-chunks", type=int, default=2048)
     ap.add_argument("--beam", type=int, default=1)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--sweep-chunks", type=int, default=1000000, help="N > 1: size of the ONE fixed batch that is sharded")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-event-path", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip raw_greedy_1k / event_only / depth_3_2 (N = 1)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling second figure")
+    ap.add_argument("--single-process", action="store_true", help="N > 1 through ShardedBasecaller instead of torchrun ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1 and args.single_process:
+        run_single_process(args)
         return
     if world == 1 and args.gpus > 1:
         # convenience: re-exec under torchrun when called as `python bench.py --gpus N`

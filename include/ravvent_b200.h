@@ -141,9 +141,11 @@ int rvb_beam(rvb_model_t *m, const float *d_raw, int t_raw, const float *d_event
              int32_t *d_pred_ids, float *d_scores, int32_t *d_step_ids, int32_t *d_parent_ids,
              int32_t *d_steps, void *stream);
 
-/* Host-buffer variants (the reference-facing call: numpy in, numpy out).
- * Pinned staging, H2D, compute, D2H and a final stream sync all happen inside.
- * h_ids [B,S] / h_scores [B,S] are beam slot 0; *h_steps = T. */
+/* Host-buffer variant (the reference-facing call: numpy in, numpy out).  The batch is processed in waves through
+ * two device I/O sets and three streams: while wave k computes, wave k+1 is staged and copied in and wave k-1 is
+ * copied out.  Pageable caller memory goes through the handle's pinned staging buffers (chunked memcpy on the
+ * calling thread); page-locked caller memory is copied from / to directly.  Returns after the last wave has
+ * landed in h_ids [B,S] / h_scores [B,S] (beam slot 0); *h_steps = T. */
 int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, const float *h_event, int t_event,
                   int64_t batch, int beam_width, int max_output_len,
                   int32_t *h_ids, float *h_scores, int32_t *h_steps);

@@ -15,6 +15,7 @@ from .basecaller import Basecaller
 from . import data_loader
 from .merger import Merger, SeqLogitsPair
 from .data_loader import nuc_tk
+from .sharding import ShardedBasecaller, shard_range
 
 __all__ = ["Basecaller", "EventDetector", "Event", "Merger", "SeqLogitsPair", "RavventError", "data_loader", "nuc_tk",
-           "device_count", "launch_count"]
+           "device_count", "launch_count", "ShardedBasecaller", "shard_range"]

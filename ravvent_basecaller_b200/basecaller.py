@@ -113,6 +113,11 @@ class Basecaller:
             raw, event = None, input_data
         return raw, event
 
+    @staticmethod
+    def _same_batch(raw, event):
+        if raw is not None and event is not None and raw.shape[0] != event.shape[0]:
+            raise ValueError(f"raw and event batches differ: {raw.shape[0]} vs {event.shape[0]}")
+
     def _dev(self, x, feat):
         if x is None:
             return None, 0
@@ -141,6 +146,7 @@ class Basecaller:
         raw, event = self._split(input_data)
         raw, t_raw = self._dev(raw, 1)
         event, t_ev = self._dev(event, 5)
+        self._same_batch(raw, event)
         B = int((raw if raw is not None else event).shape[0])
         Tm = t_raw + t_ev
         with torch.cuda.device(self.device):
@@ -160,6 +166,7 @@ class Basecaller:
         raw, event = self._split(input_data)
         raw, t_raw = self._dev(raw, 1)
         event, t_ev = self._dev(event, 5)
+        self._same_batch(raw, event)
         B = int((raw if raw is not None else event).shape[0])
         S = max(int(max_output_len) - 1, 0)
         with torch.cuda.device(self.device):
@@ -183,6 +190,11 @@ class Basecaller:
             raw, event = self._split(input_data)
             raw = None if raw is None else np.ascontiguousarray(raw, dtype=np.float32)
             event = None if event is None else np.ascontiguousarray(event, dtype=np.float32)
+            for x, feat in ((raw, 1), (event, 5)):          # the C side trusts these shapes: same checks as _dev()
+                if x is not None and (x.ndim != 3 or x.shape[-1] != feat):
+                    raise ValueError(f"expected input of shape [batch, time, {feat}], got {tuple(x.shape)}")
+            if raw is not None and event is not None and raw.shape[0] != event.shape[0]:
+                raise ValueError(f"raw and event batches differ: {raw.shape[0]} vs {event.shape[0]}")
             B = int((raw if raw is not None else event).shape[0])
             ids = np.empty((B, S), dtype=np.int32)
             scores = np.empty((B, S), dtype=np.float32)
@@ -196,6 +208,7 @@ class Basecaller:
         raw, event = self._split(input_data)
         raw, t_raw = self._dev(raw, 1)
         event, t_ev = self._dev(event, 5)
+        self._same_batch(raw, event)
         B = int((raw if raw is not None else event).shape[0])
         with torch.cuda.device(self.device):
             ids = torch.empty((B, S, W), dtype=torch.int32, device=self.device)

@@ -82,12 +82,12 @@ struct rvb_model {
     uint16_t *enc_out16 = nullptr;             // fp16 copy of enc_out (reduced-precision mode only)
     uint8_t *mask = nullptr;
     int32_t *step_ids = nullptr, *parent_ids = nullptr;
-    // host-variant device buffers
-    size_t hb_cap = 0;
-    float *hb_raw = nullptr, *hb_ev = nullptr, *hb_scores = nullptr;
-    int32_t *hb_ids = nullptr, *hb_steps = nullptr;
+    // host-buffer variant: double-buffered I/O sets, pinned staging, copy streams (HostPipe, below)
+    struct HostPipe *pipe = nullptr;
     cudaStream_t hstream = nullptr;
     std::vector<void *> owned;
+    std::vector<void *> wowned;                // packed weight buffers: released and rebuilt by every rvb_model_finalize
+    bool in_finalize = false;
 };
 
 template <typename T>
@@ -95,7 +95,7 @@ static int dmalloc(rvb_model *m, T **p, size_t n) {
     void *q = nullptr;
     cudaError_t e = cudaMalloc(&q, n * sizeof(T));
     if (e != cudaSuccess) return fail(RVB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
-    m->owned.push_back(q);
+    (m->in_finalize ? m->wowned : m->owned).push_back(q);
     *p = reinterpret_cast<T *>(q);
     return RVB_OK;
 }
@@ -103,7 +103,11 @@ static void dfree(rvb_model *m, void *p) {
     if (!p) return;
     for (auto &q : m->owned)
         if (q == p) { cudaFree(q); q = nullptr; }
+    for (auto &q : m->wowned)
+        if (q == p) { cudaFree(q); q = nullptr; }
 }
+
+static void host_pipe_destroy(rvb_model *m);
 
 extern "C" int rvb_version(void) { return 100; }
 extern "C" const char *rvb_last_error(void) { return err_buf(); }
@@ -154,7 +158,9 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
 extern "C" int rvb_model_destroy(rvb_model_t *m) {
     if (!m) return RVB_OK;
     cudaSetDevice(m->device);
+    host_pipe_destroy(m);
     for (void *q : m->owned) if (q) cudaFree(q);
+    for (void *q : m->wowned) if (q) cudaFree(q);
     if (m->hstream) cudaStreamDestroy(m->hstream);
     delete m;
     return RVB_OK;
@@ -187,9 +193,24 @@ static int upload(rvb_model *m, float **dst, const std::vector<float> &v) {
     return RVB_OK;
 }
 
+static int finalize_impl(rvb_model *m);
+
 extern "C" int rvb_model_finalize(rvb_model_t *m) {
     if (!m) return fail(RVB_ERR_ARG, "null model");
     RVB_CUDA(cudaSetDevice(m->device));
+    // a second load_weights on the same handle: drop the previous packed copies first (nothing may be in flight)
+    RVB_CUDA(cudaDeviceSynchronize());
+    for (void *q : m->wowned) if (q) cudaFree(q);
+    m->wowned.clear();
+    m->d_abort = nullptr;
+    m->finalized = false;
+    m->in_finalize = true;
+    const int st = finalize_impl(m);
+    m->in_finalize = false;
+    return st;
+}
+
+static int finalize_impl(rvb_model *m) {
     const char *enc_name[2] = {"encoder_raw", "encoder_event"};
     const int enc_feat[2] = {1, 5};
     const char *dir_name[2] = {"forward", "backward"};
@@ -567,6 +588,83 @@ __global__ void slot0_kernel(const int32_t *ids, const float *sc, long long n, i
 
 extern "C" int rvb_model_check(rvb_model_t *m);
 
+// Host-buffer pipeline of rvb_beam_host: two device I/O sets, two pinned staging sets, three streams.
+// Wave k: [CPU copy user -> pinned in (pageable callers only)] -> H2D on s_in -> compute on s_comp -> slot-0 extraction ->
+// D2H on s_out -> [CPU copy pinned out -> user].  Wave k+1's staging + H2D and wave k-1's D2H + unstaging overlap wave
+// k's compute; the compute itself is serial (one workspace per handle).
+struct HostPipe {
+    size_t in_floats = 0, out_words = 0;           // per set
+    float *d_in[2] = {nullptr, nullptr};
+    int32_t *d_out[2] = {nullptr, nullptr};        // [ids0 | scores0 | steps]
+    float *p_in[2] = {nullptr, nullptr};           // pinned staging
+    int32_t *p_out[2] = {nullptr, nullptr};
+    float *d_full_sc = nullptr; int32_t *d_full_ids = nullptr; size_t full_words = 0;   // [wave,S,W] search outputs
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+};
+
+static bool host_ptr_is_pinned(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int host_pipe_prepare(rvb_model *m, size_t in_floats, size_t out_words, size_t full_words) {
+    if (!m->pipe) m->pipe = new HostPipe();
+    HostPipe *hp = m->pipe;
+    if (!hp->s_in) {
+        RVB_CUDA(cudaStreamCreateWithFlags(&hp->s_in, cudaStreamNonBlocking));
+        RVB_CUDA(cudaStreamCreateWithFlags(&hp->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            RVB_CUDA(cudaEventCreateWithFlags(&hp->h2d_done[i], cudaEventDisableTiming));
+            RVB_CUDA(cudaEventCreateWithFlags(&hp->comp_done[i], cudaEventDisableTiming));
+            RVB_CUDA(cudaEventCreateWithFlags(&hp->d2h_done[i], cudaEventDisableTiming));
+        }
+    }
+    if (in_floats > hp->in_floats) {
+        for (int i = 0; i < 2; ++i) {
+            dfree(m, hp->d_in[i]);
+            RVB_CHECK(dmalloc(m, &hp->d_in[i], in_floats));
+            if (hp->p_in[i]) cudaFreeHost(hp->p_in[i]);
+            RVB_CUDA(cudaMallocHost(&hp->p_in[i], in_floats * sizeof(float)));
+        }
+        hp->in_floats = in_floats;
+    }
+    if (out_words > hp->out_words) {
+        for (int i = 0; i < 2; ++i) {
+            dfree(m, hp->d_out[i]);
+            RVB_CHECK(dmalloc(m, &hp->d_out[i], out_words));
+            if (hp->p_out[i]) cudaFreeHost(hp->p_out[i]);
+            RVB_CUDA(cudaMallocHost(&hp->p_out[i], out_words * sizeof(int32_t)));
+        }
+        hp->out_words = out_words;
+    }
+    if (full_words > hp->full_words) {
+        dfree(m, hp->d_full_sc); dfree(m, hp->d_full_ids);
+        RVB_CHECK(dmalloc(m, &hp->d_full_sc, full_words));
+        RVB_CHECK(dmalloc(m, &hp->d_full_ids, full_words));
+        hp->full_words = full_words;
+    }
+    return RVB_OK;
+}
+
+static void host_pipe_destroy(rvb_model *m) {
+    HostPipe *hp = m->pipe;
+    if (!hp) return;
+    for (int i = 0; i < 2; ++i) {
+        if (hp->p_in[i]) cudaFreeHost(hp->p_in[i]);
+        if (hp->p_out[i]) cudaFreeHost(hp->p_out[i]);
+        if (hp->h2d_done[i]) cudaEventDestroy(hp->h2d_done[i]);
+        if (hp->comp_done[i]) cudaEventDestroy(hp->comp_done[i]);
+        if (hp->d2h_done[i]) cudaEventDestroy(hp->d2h_done[i]);
+    }
+    if (hp->s_in) cudaStreamDestroy(hp->s_in);
+    if (hp->s_out) cudaStreamDestroy(hp->s_out);
+    delete hp;
+    m->pipe = nullptr;
+}
+
 extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, const float *h_event, int t_event, int64_t batch,
                              int beam_width, int max_output_len, int32_t *h_ids, float *h_scores, int32_t *h_steps) {
     int Tm = 0;
@@ -580,42 +678,83 @@ extern "C" int rvb_beam_host(rvb_model_t *m, const float *h_raw, int t_raw, cons
     if (W < 1 || W > 9) return fail(RVB_ERR_ARG, "beam_width must be in [1,9]");
     RVB_CUDA(cudaSetDevice(m->device));
     if (!m->hstream) RVB_CUDA(cudaStreamCreateWithFlags(&m->hstream, cudaStreamNonBlocking));
-    cudaStream_t s = m->hstream;
-    // device-side I/O for one wave at a time (handle-owned, grown on demand)
+    cudaStream_t sc = m->hstream;
+    if (!need_raw) t_raw = 0;
+    if (!need_ev) t_event = 0;
     const size_t wv = (size_t)m->wave;
-    const size_t need = wv * ((size_t)t_raw + (size_t)t_event * 5 + (size_t)S * W * 2 + (size_t)S * 2) + 64;
-    if (need > m->hb_cap) {
-        dfree(m, m->hb_raw);
-        RVB_CHECK(dmalloc(m, &m->hb_raw, need));
-        m->hb_cap = need;
-    }
-    float *d_raw = m->hb_raw;
-    float *d_ev = d_raw + wv * t_raw;
-    float *d_sc = d_ev + wv * t_event * 5;
-    int32_t *d_ids = reinterpret_cast<int32_t *>(d_sc + wv * S * W);
-    float *d_sc0 = reinterpret_cast<float *>(d_ids + wv * S * W);
-    int32_t *d_ids0 = reinterpret_cast<int32_t *>(d_sc0 + wv * S);
-    int32_t *d_steps = d_ids0 + wv * S;
-    RVB_CUDA(cudaMemsetAsync(d_steps, 0, sizeof(int32_t), s));
-    for (int64_t b0 = 0; b0 < batch; b0 += m->wave) {
-        const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
-        if (need_raw) RVB_CUDA(cudaMemcpyAsync(d_raw, h_raw + (size_t)b0 * t_raw, (size_t)nb * t_raw * sizeof(float), cudaMemcpyHostToDevice, s));
-        if (need_ev) RVB_CUDA(cudaMemcpyAsync(d_ev, h_event + (size_t)b0 * t_event * 5, (size_t)nb * t_event * 5 * sizeof(float), cudaMemcpyHostToDevice, s));
-        int32_t *tmp_steps = d_steps + 1;
-        RVB_CHECK(search(m, need_raw ? d_raw : nullptr, t_raw, need_ev ? d_ev : nullptr, t_event, nb, W, max_output_len, true,
-                         d_ids, nullptr, d_sc, nullptr, nullptr, tmp_steps, s));
-        // fold this wave's T into the running maximum and keep slot 0 only
+    const size_t raw_f = wv * (size_t)t_raw, ev_f = wv * (size_t)t_event * 5;
+    const size_t out_w = wv * (size_t)S * 2 + 4;
+    RVB_CHECK(host_pipe_prepare(m, raw_f + ev_f + 4, out_w, wv * (size_t)S * W));
+    HostPipe *hp = m->pipe;
+    // a caller that already holds page-locked memory is copied from / to directly; pageable memory goes through the pinned
+    // staging sets (a cudaMemcpyAsync on pageable memory would serialise against the running wave)
+    const bool stage_in = !(host_ptr_is_pinned(need_raw ? h_raw : nullptr) && host_ptr_is_pinned(need_ev ? h_event : nullptr));
+    const bool stage_out = !(host_ptr_is_pinned(h_ids) && host_ptr_is_pinned(h_scores));
+    const int64_t nw = (batch + m->wave - 1) / m->wave;
+    auto wave_rows = [&](int64_t k) { return (int)std::min<int64_t>(m->wave, batch - k * m->wave); };
+
+    auto issue_h2d = [&](int64_t k) -> int {
+        const int set = (int)(k & 1), nb = wave_rows(k);
+        const size_t b0 = (size_t)k * wv;
+        if (k >= 2) {
+            if (stage_in) RVB_CUDA(cudaEventSynchronize(hp->h2d_done[set]));          // pinned set: its previous H2D has left
+            RVB_CUDA(cudaStreamWaitEvent(hp->s_in, hp->comp_done[set], 0));          // device set: wave k-2 consumed it
+        }
+        float *d_raw = hp->d_in[set], *d_ev = d_raw + raw_f;
+        const float *src_raw = need_raw ? h_raw + b0 * t_raw : nullptr;
+        const float *src_ev = need_ev ? h_event + b0 * t_event * 5 : nullptr;
+        if (stage_in) {
+            float *p_raw = hp->p_in[set], *p_ev = p_raw + raw_f;
+            if (need_raw) { memcpy(p_raw, src_raw, (size_t)nb * t_raw * sizeof(float)); src_raw = p_raw; }
+            if (need_ev) { memcpy(p_ev, src_ev, (size_t)nb * t_event * 5 * sizeof(float)); src_ev = p_ev; }
+        }
+        if (need_raw) RVB_CUDA(cudaMemcpyAsync(d_raw, src_raw, (size_t)nb * t_raw * sizeof(float), cudaMemcpyHostToDevice, hp->s_in));
+        if (need_ev) RVB_CUDA(cudaMemcpyAsync(d_ev, src_ev, (size_t)nb * t_event * 5 * sizeof(float), cudaMemcpyHostToDevice, hp->s_in));
+        RVB_CUDA(cudaEventRecord(hp->h2d_done[set], hp->s_in));
+        return RVB_OK;
+    };
+    auto finish = [&](int64_t k) -> int {                 // wave k's results are in the pinned / user buffers after this
+        const int set = (int)(k & 1), nb = wave_rows(k);
+        const size_t b0 = (size_t)k * wv, n = (size_t)nb * S;
+        RVB_CUDA(cudaEventSynchronize(hp->d2h_done[set]));
+        const int32_t *po = hp->p_out[set];
+        if (stage_out) {
+            memcpy(h_ids + b0 * S, po, n * sizeof(int32_t));
+            memcpy(h_scores + b0 * S, po + wv * S, n * sizeof(float));
+        }
+        const int32_t wave_steps = po[2 * wv * S];
+        if (wave_steps > *h_steps) *h_steps = wave_steps;
+        return RVB_OK;
+    };
+
+    RVB_CHECK(issue_h2d(0));
+    for (int64_t k = 0; k < nw; ++k) {
+        const int set = (int)(k & 1), nb = wave_rows(k);
+        const size_t b0 = (size_t)k * wv;
         const long long n = (long long)nb * S;
-        slot0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_ids, d_sc, n, W, d_ids0, d_sc0);
+        if (k + 1 < nw) RVB_CHECK(issue_h2d(k + 1));       // staging + H2D of the next wave run under this wave's compute
+        int32_t *d_ids0 = hp->d_out[set];
+        float *d_sc0 = reinterpret_cast<float *>(d_ids0 + wv * S);
+        int32_t *d_steps = d_ids0 + 2 * wv * S;
+        RVB_CUDA(cudaStreamWaitEvent(sc, hp->h2d_done[set], 0));
+        if (k >= 2) RVB_CUDA(cudaStreamWaitEvent(sc, hp->d2h_done[set], 0));          // output set: wave k-2 has been read back
+        float *d_raw = hp->d_in[set], *d_ev = d_raw + raw_f;
+        RVB_CHECK(search(m, need_raw ? d_raw : nullptr, t_raw, need_ev ? d_ev : nullptr, t_event, nb, W, max_output_len, true,
+                         hp->d_full_ids, nullptr, hp->d_full_sc, nullptr, nullptr, d_steps, sc));
+        slot0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc>>>(hp->d_full_ids, hp->d_full_sc, n, W, d_ids0, d_sc0);
         RVB_LAUNCH_CHECK();
         count_launch();
-        RVB_CUDA(cudaMemcpyAsync(h_ids + (size_t)b0 * S, d_ids0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        RVB_CUDA(cudaMemcpyAsync(h_scores + (size_t)b0 * S, d_sc0, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-        int32_t wave_steps = 0;
-        RVB_CUDA(cudaMemcpyAsync(&wave_steps, tmp_steps, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        RVB_CUDA(cudaStreamSynchronize(s));
-        if (wave_steps > *h_steps) *h_steps = wave_steps;
+        RVB_CUDA(cudaEventRecord(hp->comp_done[set], sc));
+        RVB_CUDA(cudaStreamWaitEvent(hp->s_out, hp->comp_done[set], 0));
+        int32_t *po = hp->p_out[set];
+        RVB_CUDA(cudaMemcpyAsync(stage_out ? po : h_ids + b0 * S, d_ids0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, hp->s_out));
+        RVB_CUDA(cudaMemcpyAsync(stage_out ? reinterpret_cast<void *>(po + wv * S) : reinterpret_cast<void *>(h_scores + b0 * S), d_sc0,
+                                 n * sizeof(float), cudaMemcpyDeviceToHost, hp->s_out));
+        RVB_CUDA(cudaMemcpyAsync(po + 2 * wv * S, d_steps, sizeof(int32_t), cudaMemcpyDeviceToHost, hp->s_out));
+        RVB_CUDA(cudaEventRecord(hp->d2h_done[set], hp->s_out));
+        if (k >= 1) RVB_CHECK(finish(k - 1));
     }
+    RVB_CHECK(finish(nw - 1));
     return rvb_model_check(m);
 }
 

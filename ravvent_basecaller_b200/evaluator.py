@@ -26,13 +26,16 @@ from .merger import Merger
 
 
 class RavventPerformanceEvaluator():
-    def __init__(self, merger_scores_id=0, beam_width=5, device=None, precision='fp32'):
+    def __init__(self, merger_scores_id=0, beam_width=5, device=None, precision='fp32', encoder_depth=2, decoder_depth=1):
+        """encoder_depth / decoder_depth: what the reference hard-codes in setup_basecaller (2, 1 at
+        ravvent_performance_evaluator.py:99-100) or edits as module constants (ravvent_mapping_evaluator.py:16-17)."""
         self.merger = Merger(scores_id=merger_scores_id, device=device)
         self.stride = 6
         self.basecaller = None
         self.beam_width = int(beam_width)
         self.device = device
         self.precision = precision
+        self.encoder_depth, self.decoder_depth = int(encoder_depth), int(decoder_depth)
 
     def _split_into_chunks(self, arr, def_chunk_size):
         """Chunks of def_chunk_size rows, the last one shorter (ravvent_performance_evaluator.py:19-22)."""
@@ -159,7 +162,7 @@ class RavventPerformanceEvaluator():
         if mode == 1:
             self.basecaller = Basecaller(
                 enc_units=128, dec_units=128, batch_sz=128, tokenizer=dl.nuc_tk, input_data_type=data_type,
-                input_padding_value=dl.INPUT_PADDING, encoder_depth=2, decoder_depth=1, rnn_type='bilstm',
+                input_padding_value=dl.INPUT_PADDING, encoder_depth=self.encoder_depth, decoder_depth=self.decoder_depth, rnn_type='bilstm',
                 attention_type='luong', teacher_forcing=0.5, device=self.device, precision=self.precision)
         self.basecaller.compile(optimizer=None)
         self.basecaller.load_weights(weights_path)
@@ -198,8 +201,10 @@ class RavventMappingEvaluator(RavventPerformanceEvaluator):
     the prediction as FASTQ, maps them with `minimap2 -x map-ont -c` and returns the identity dictionary.  The file
     writers and the PAF reader are static so they can be used (and tested) without a GPU."""
 
-    def __init__(self, merger_scores_id=0, beam_width=5, device=None, precision='fp32', work_dir='temp'):
-        super().__init__(merger_scores_id, beam_width, device, precision)
+    def __init__(self, merger_scores_id=0, beam_width=5, device=None, precision='fp32', work_dir='temp',
+                 encoder_depth=1, decoder_depth=1):
+        # defaults = the reference's module constants ENCODER_DEPTH = DECODER_DEPTH = 1, BEAM_WIDTH = 5 (:15-17)
+        super().__init__(merger_scores_id, beam_width, device, precision, encoder_depth, decoder_depth)
         self.work_dir = Path(work_dir)
 
     @staticmethod

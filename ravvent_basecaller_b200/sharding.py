@@ -35,3 +35,87 @@ def run_sharded(fn, inputs, rank: int, world: int, group=None):
     lo, hi = shard_range(n, rank, world)
     shard = tuple(x[lo:hi] for x in inputs) if isinstance(inputs, (tuple, list)) else inputs[lo:hi]
     return gather_in_order(np.asarray(fn(shard)), n, group)
+
+
+class ShardedBasecaller:
+    """One process, every GPU of the box: the multi-GPU form of Basecaller.beam_search_prediction
+    (BASELINE.json north_star: "partitioned across the 8 B200s of one box by read batch on per-GPU streams
+    with a host-side gather"; replaces the single predict loop of ravvent_performance_evaluator.py:35-70).
+
+    One Basecaller handle per device (its own streams, pinned staging ring and workspace), weights
+    replicated (5 MB).  A host batch is cut into contiguous shards (shard_range); one host thread per
+    device drives rvb_beam_host (ctypes releases the GIL for the whole call) and writes its rows straight
+    into ONE pair of host arrays, so the results are already gathered in input order when the threads join.
+    There is no collective: nothing needs reducing."""
+
+    def __init__(self, *args, devices=None, **kwargs):
+        import torch
+        from .basecaller import Basecaller
+        if devices is None:
+            devices = list(range(torch.cuda.device_count()))
+        if not devices:
+            raise ValueError("ShardedBasecaller needs at least one CUDA device")
+        kwargs.pop("device", None)
+        self.devices = [int(d) for d in devices]
+        self.replicas = [Basecaller(*args, device=d, **kwargs) for d in self.devices]
+
+    def compile(self, *args, **kwargs):
+        return None
+
+    def load_weights(self, source=None, **kw):
+        for r in self.replicas:
+            r.load_weights(source, **kw)
+        return self
+
+    def tokens_to_nuc_sequences(self, ids):
+        return self.replicas[0].tokens_to_nuc_sequences(ids)
+
+    def beam_search_prediction(self, input_data, beam_width, max_output_len):
+        """Host (numpy) inputs -> (ids [B,T] int32, scores [B,T] float32) in input order, as Basecaller returns them."""
+        import ctypes as C
+        import threading
+        from . import _lib
+        r0 = self.replicas[0]
+        raw, event = r0._split(input_data)
+        raw = None if raw is None else np.ascontiguousarray(raw, dtype=np.float32)
+        event = None if event is None else np.ascontiguousarray(event, dtype=np.float32)
+        for x, feat in ((raw, 1), (event, 5)):
+            if x is not None and (x.ndim != 3 or x.shape[-1] != feat):
+                raise ValueError(f"expected input of shape [batch, time, {feat}], got {tuple(x.shape)}")
+        r0._same_batch(raw, event)
+        B = int((raw if raw is not None else event).shape[0])
+        S = max(int(max_output_len) - 1, 0)
+        ids = np.empty((B, S), dtype=np.int32)
+        scores = np.empty((B, S), dtype=np.float32)
+        world = len(self.replicas)
+        steps = [0] * world
+        errors = [None] * world
+
+        def work(k):
+            try:
+                lo, hi = shard_range(B, k, world)
+                if hi == lo:
+                    return
+                st = C.c_int32(0)
+                rep = self.replicas[k]
+                _lib.check(_lib.lib.rvb_beam_host(
+                    rep._h, None if raw is None else raw[lo:hi].ctypes.data, 0 if raw is None else raw.shape[1],
+                    None if event is None else event[lo:hi].ctypes.data, 0 if event is None else event.shape[1],
+                    hi - lo, int(beam_width), int(max_output_len), ids[lo:hi].ctypes.data, scores[lo:hi].ctypes.data, C.byref(st)))
+                steps[k] = st.value
+            except BaseException as e:          # re-raised on the calling thread
+                errors[k] = e
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(world)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for e in errors:
+            if e is not None:
+                raise e
+        # T = steps dynamic_decode would have executed on the WHOLE batch = the longest any shard needed.  Every shard
+        # computed all S steps (steps past its own T hold what dynamic_decode would have appended: end tokens, unchanged
+        # scores), so the common prefix [:, :T] is exactly the single-GPU result.
+        T = max(steps) if B else 0
+        return ids[:, :T], scores[:, :T]
