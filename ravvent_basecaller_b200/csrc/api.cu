@@ -69,7 +69,8 @@ struct rvb_model {
     float *d_wg1 = nullptr, *d_b1 = nullptr;
     // wave-level beam decoder (decoder_wave.cu): tf32 hi/lo transposed weights + Keras-order token rows + workspace
     float *dw_wg[2] = {nullptr, nullptr}, *dw_wm[2] = {nullptr, nullptr}, *dw_wa[2] = {nullptr, nullptr}, *dw_wtok = nullptr, *dw_ws = nullptr;
-    uint16_t *dw_wg16[2] = {nullptr, nullptr}, *dw_wm16[2] = {nullptr, nullptr};
+    uint16_t *dw_wg16[2] = {nullptr, nullptr}, *dw_wm16[2] = {nullptr, nullptr}, *dw_wg1_16[2] = {nullptr, nullptr};
+    float *dw_wg1[2] = {nullptr, nullptr}, *dw_b1 = nullptr;
     size_t dw_ws_rows = 0;
     bool dec_wave = false;
     float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
@@ -150,7 +151,7 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     const char *r = getenv("RVB_REC");
     m->rec_tc = m->use_tc && !(r && strcmp(r, "ffma") == 0);
     const char *dv = getenv("RVB_DECODER");
-    m->dec_wave = m->use_tc && decoder_depth == 1 && !(dv && strcmp(dv, "persistent") == 0);
+    m->dec_wave = m->use_tc && !(dv && strcmp(dv, "persistent") == 0);
     *out = m;
     return RVB_OK;
 }
@@ -352,6 +353,20 @@ static int finalize_impl(rvb_model *m) {
             RVB_CHECK(prep(wmT, UNITS, ENC_OUT, m->dw_wm, m->dw_wm16));
             RVB_CHECK(prep(Wa->data, UNITS + ENC_OUT, UNITS, m->dw_wa));
             RVB_CHECK(upload(m, &m->dw_wtok, wtk));
+            if (m->dec_depth == 2) {
+                // second stacked cell: [kernel (input = h of cell 0) ; recurrent kernel] as one [256,512] weight, [unit][gate] columns
+                const HostTensor *W1, *U1, *B1;
+                RVB_CHECK(get_w(m, "decoder/cell1/kernel", UNITS, GATES, &W1));
+                RVB_CHECK(get_w(m, "decoder/cell1/recurrent_kernel", UNITS, GATES, &U1));
+                RVB_CHECK(get_w(m, "decoder/cell1/bias", GATES, -1, &B1));
+                std::vector<float> w1cat((size_t)2 * UNITS * GATES), b1v(GATES);
+                for (int k = 0; k < 2 * UNITS; ++k)
+                    for (int n = 0; n < GATES; ++n)
+                        w1cat[(size_t)k * GATES + (n % UNITS) * 4 + n / UNITS] = k < UNITS ? W1->data[(size_t)k * GATES + n] : U1->data[(size_t)(k - UNITS) * GATES + n];
+                for (int n = 0; n < GATES; ++n) b1v[(n % UNITS) * 4 + n / UNITS] = B1->data[n];
+                RVB_CHECK(prep(w1cat, 2 * UNITS, GATES, m->dw_wg1, m->dw_wg1_16));
+                RVB_CHECK(upload(m, &m->dw_b1, b1v));
+            }
         }
         RVB_CHECK(upload(m, &m->d_wmem, Wm->data));
         std::vector<float> wmT((size_t)UNITS * ENC_OUT);
@@ -528,7 +543,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             const size_t rows = (size_t)m->wave * W;
             if (rows > m->dw_ws_rows) {
                 dfree(m, m->dw_ws);
-                RVB_CHECK(dmalloc(m, &m->dw_ws, decw::workspace_floats((long long)rows)));
+                RVB_CHECK(dmalloc(m, &m->dw_ws, decw::workspace_floats((long long)rows, m->dec_depth)));
                 m->dw_ws_rows = rows;
             }
             decw::Params q{};
@@ -536,6 +551,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
             q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];
             q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
+            q.wg1_16_hi = m->dw_wg1_16[0]; q.wg1_16_lo = m->dw_wg1_16[1]; q.b1 = m->dw_b1; q.depth = m->dec_depth;
             q.B = nb; q.Tm = Tm; q.W = W; q.S = S;
             q.ids = d_ids + (size_t)b0 * S * W; q.scores = d_scores + (size_t)b0 * S * W;
             q.step_ids = d_step_ids ? d_step_ids + (size_t)b0 * S * W : m->step_ids;

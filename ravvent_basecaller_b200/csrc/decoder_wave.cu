@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
                                                         float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent,
                                                         int32_t *first_done, float *scores, int32_t *step_ids, int32_t *parent_ids,
                                                         int B, int W, int S, int t, const float *__restrict__ xa, float *__restrict__ X,
-                                                        uint16_t *__restrict__ x_hi, uint16_t *__restrict__ x_lo) {
+                                                        uint16_t *__restrict__ x_hi, uint16_t *__restrict__ x_lo,
+                                                        const float *__restrict__ h0, uint16_t *__restrict__ x1_hi, uint16_t *__restrict__ x1_lo) {
     __shared__ float a_s[4][WMAX * UNITS];
     __shared__ float lg_s[4][WMAX * 8];
     __shared__ float wfc_s[UNITS * VOCAB];
@@ -233,20 +234,23 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     const unsigned allfin = __ballot_sync(0xffffffffu, lane >= W || nfin);
     if (lane == 0 && allfin == 0xffffffffu && first_done[b] == S) first_done[b] = t;
     // input of the next step's cell GEMM, gathered through the parents chosen just now: X[r] = [attention[src] | h[src]]
+    // (two stacked cells: h of cell 0 comes from h0, and the top cell's h goes into the second half of X1[r] = [h0_new[r] | h1[src]])
     for (int k = 0; k < W; ++k) {
         const size_t src = r0 + __shfl_sync(0xffffffffu, par, k);
         const float4 va = __ldg(reinterpret_cast<const float4 *>(att + src * UNITS) + lane);
-        const float4 vh = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + lane);
+        const float4 vtop = __ldg(reinterpret_cast<const float4 *>(xa + src * (3 * UNITS)) + lane);
+        const float4 vh = (h0 != nullptr) ? __ldg(reinterpret_cast<const float4 *>(h0 + src * UNITS) + lane) : vtop;
         if (x_hi != nullptr) {                 // fp16 hi / lo planes (the cell GEMM runs on the fp16 pipe)
-            auto put = [&](const float4 v, size_t o) {
+            auto put = [&](uint16_t *hi, uint16_t *lo, const float4 v, size_t o) {
                 const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
                 const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
                 const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
-                *reinterpret_cast<uint2 *>(x_hi + o) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                *reinterpret_cast<uint2 *>(x_lo + o) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                *reinterpret_cast<uint2 *>(hi + o) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                *reinterpret_cast<uint2 *>(lo + o) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
             };
-            put(va, (r0 + k) * (2 * UNITS) + 4 * lane);
-            put(vh, (r0 + k) * (2 * UNITS) + UNITS + 4 * lane);
+            put(x_hi, x_lo, va, (r0 + k) * (2 * UNITS) + 4 * lane);
+            put(x_hi, x_lo, vh, (r0 + k) * (2 * UNITS) + UNITS + 4 * lane);
+            if (x1_hi != nullptr) put(x1_hi, x1_lo, vtop, (r0 + k) * (2 * UNITS) + UNITS + 4 * lane);
         } else {
             float4 *dst = reinterpret_cast<float4 *>(X + (r0 + k) * (2 * UNITS));
             dst[lane] = va;
@@ -291,9 +295,10 @@ __global__ void finalize_kernel(const int32_t *step_ids, const int32_t *parent_i
     if (k == 0) atomicMax(steps, min(first_done[b] + 1, S));
 }
 
-size_t workspace_floats(long long rows) {
+size_t workspace_floats(long long rows, int depth) {
     // X 256 | Z 512 | XA 384 | Q 256 | ATT 128 | c x2 256 | lp 1  + ints: fin len tok parent 4 + first_done
-    return (size_t)rows * (256 + 512 + 384 + 256 + 128 + 256 + 1 + 4 + 1) + 64;
+    // depth 2 adds: X1 planes 256 | H0 128 | c of cell 1 x2 256
+    return (size_t)rows * (256 + 512 + 384 + 256 + 128 + 256 + 1 + 4 + 1 + (depth == 2 ? 256 + 128 + 256 : 0)) + 64 + 64;
 }
 
 int run(const Params &p, cudaStream_t s) {
@@ -304,15 +309,27 @@ int run(const Params &p, cudaStream_t s) {
     float *c0 = ATT + rows * 128, *c1 = c0 + rows * 128, *lp = c1 + rows * 128;
     int32_t *fin = reinterpret_cast<int32_t *>(lp + rows), *len = fin + rows, *tok = len + rows, *parent = tok + rows;
     int32_t *first_done = parent + rows;
+    const bool two = p.depth == 2;
+    // depth 2 only; re-aligned to 256 bytes (the scalar arrays before it leave any 4-byte offset): TMA source + vector stores
+    float *X1 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(first_done + rows) + 255) & ~uintptr_t(255));
+    float *H0 = X1 + rows * 256, *d0 = H0 + rows * 128, *d1 = d0 + rows * 128;
+    uint16_t *x1_hi = reinterpret_cast<uint16_t *>(X1), *x1_lo = x1_hi + rows * 256;
     // fp16-plane operands share the X / Z regions: X = [hi plane | lo plane] of [rows][256] halves, Z holds the h planes
     static const bool f16_off = getenv("RVB_DECODER_GEMM") && strcmp(getenv("RVB_DECODER_GEMM"), "tf32") == 0;
     const bool f16 = p.wg16_hi != nullptr && p.wm16_hi != nullptr && !f16_off;
+    if (two && (!f16 || p.wg1_16_hi == nullptr || p.b1 == nullptr))
+        return fail(RVB_ERR_STATE, "decoder_wave: decoder_depth 2 needs the fp16-plane weights");
     uint16_t *x_hi = reinterpret_cast<uint16_t *>(X), *x_lo = x_hi + rows * 256;
     uint16_t *h_hi = reinterpret_cast<uint16_t *>(Z), *h_lo = h_hi + rows * 128;
     RVB_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * rows * 256, s));          // step 0: attention = h = 0
     RVB_CUDA(cudaMemsetAsync(XA, 0, sizeof(float) * rows * 384, s));
     RVB_CUDA(cudaMemsetAsync(ATT, 0, sizeof(float) * rows * 128, s));
     RVB_CUDA(cudaMemsetAsync(c0, 0, sizeof(float) * rows * 128, s));
+    if (two) {
+        RVB_CUDA(cudaMemsetAsync(X1, 0, sizeof(float) * rows * 256, s));         // h of both cells = 0
+        RVB_CUDA(cudaMemsetAsync(H0, 0, sizeof(float) * rows * 128, s));
+        RVB_CUDA(cudaMemsetAsync(d0, 0, sizeof(float) * rows * 128, s));
+    }
     // profiling (bench.py): the attention kernel is timed per launch as its own kind, everything else as "decoder"
     {
         ProfScope ps(KK_DECODER, s);
@@ -326,8 +343,18 @@ int run(const Params &p, cudaStream_t s) {
         {
             ProfScope ps(KK_DECODER, s);
             // cell update fused into the GEMM epilogue; with fp16 weight planes both GEMMs run on the fp16 pipe (3 split passes)
-            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr};
-            if (f16) {
+            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr, 0, 0};
+            if (two) {
+                // cell 0: h0 (fp32, for the next step's gather) -> H0, and as fp16 planes into the first half of X1;
+                // cell 1: X1 = [h0 | h1_prev[src]] . [W1 ; U1] + b1 with its own c ping-pong; its h is the query / attention-layer input
+                float *din = (t & 1) ? d1 : d0, *dout = (t & 1) ? d0 : d1;
+                const gemm::CellEpilogue ce0{p.wtok, tok, parent, cin, cout, H0, p.W, x1_hi, x1_lo, UNITS, 2 * UNITS};
+                const gemm::CellEpilogue ce1{p.b1, nullptr, parent, din, dout, XA, p.W, h_hi, h_lo, 0, 0};
+                RVB_CHECK(gemm::run_tc_f16(x_hi, x_lo, p.wg16_hi, p.wg16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce0));
+                RVB_CHECK(gemm::run_tc_f16(x1_hi, x1_lo, p.wg1_16_hi, p.wg1_16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce1));
+                RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s));
+                ++nl;
+            } else if (f16) {
                 RVB_CHECK(gemm::run_tc_f16(x_hi, x_lo, p.wg16_hi, p.wg16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce));
                 RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s));
             } else {
@@ -345,7 +372,8 @@ int run(const Params &p, cudaStream_t s) {
             ProfScope ps(KK_DECODER, s);
             RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
-                                                p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr);
+                                                p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr,
+                                                two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr);
             RVB_LAUNCH_CHECK();
         }
         nl += 2;

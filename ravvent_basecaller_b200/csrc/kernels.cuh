@@ -55,11 +55,12 @@ int prepare_weights(const float *W, float *hiT, float *loT, int K, int N, cudaSt
 // writes c_out[row, unit] and h into xa[row, 0:128] (row stride 384).
 struct CellEpilogue {
     const float *wtok;          // [vocab][512]: input-kernel row of the token + bias, [unit][gate] order
-    const int32_t *tok, *parent;
+    const int32_t *tok, *parent;    // tok == nullptr: row 0 of wtok for every row (a plain bias, second stacked cell)
     const float *c_in;
-    float *c_out, *xa;
+    float *c_out, *xa;          // xa: fp32 h at xa[row*xa_ld + unit] (must be non-null: it selects this epilogue)
     int W;                      // beams per snippet (parent indices are relative to the snippet's first row)
-    uint16_t *h_hi, *h_lo;      // optional fp16 hi / lo planes of h, [row][128]: the A operand of the query GEMM
+    uint16_t *h_hi, *h_lo;      // optional fp16 hi / lo planes of h at [row*h_ld + unit]: A operand of the next GEMM
+    int xa_ld, h_ld;            // row pitches in elements (0 = the depth-1 defaults 384 / 128)
 };
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
            int precision, int *abort_flag, cudaStream_t s, long long lda = 0, const CellEpilogue *cell = nullptr);
@@ -105,6 +106,9 @@ struct Params {
     const float *wa_hiT, *wa_loT;   // attention layer [384,128], transposed [128,384]
     const void *wg16_hi, *wg16_lo, *wm16_hi, *wm16_lo;   // fp16 hi / lo planes of the first two (transposed); nullptr: tf32 path
     const float *wtok;          // [7][512] kernel row of token v + bias, [unit][gate] columns
+    const void *wg1_16_hi, *wg1_16_lo;   // decoder_depth 2: fp16 hi / lo planes of [kernel ; recurrent kernel] of cell 1, transposed [512,256]
+    const float *b1;            // decoder_depth 2: bias of cell 1, [512] in [unit][gate] order
+    int depth;                  // stacked decoder cells: 1 or 2
     const float *wfc, *bfc;     // [128][7], [7]
     int B, Tm, W, S;
     int32_t *ids;               // predicted_ids [B,S,W]
@@ -114,7 +118,7 @@ struct Params {
     float *ws;                  // workspace_floats(B*W) floats
     int *abort_flag;
 };
-size_t workspace_floats(long long rows);
+size_t workspace_floats(long long rows, int depth = 1);
 int run(const Params &p, cudaStream_t stream);
 }  // namespace decw
 

@@ -533,7 +533,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     const long long R = m_tile * BM + row;
                     if (R < M) {
                         const int col0 = n_tile * PBN + c0, u0 = col0 >> 2;
-                        const float4 *tk = reinterpret_cast<const float4 *>(cell.wtok + (size_t)__ldg(cell.tok + R) * N + col0);
+                        const float4 *tk = reinterpret_cast<const float4 *>(cell.wtok + (size_t)(cell.tok != nullptr ? __ldg(cell.tok + R) : 0) * N + col0);
                         const long long src = (R / cell.W) * cell.W + __ldg(cell.parent + R);
                         const float4 ca = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0));
                         const float4 cb4 = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0 + 4));
@@ -549,7 +549,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         }
                         float4 *co = reinterpret_cast<float4 *>(cell.c_out + R * 128 + u0);
                         co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                        float4 *ho = reinterpret_cast<float4 *>(cell.xa + R * 384 + u0);
+                        float4 *ho = reinterpret_cast<float4 *>(cell.xa + R * (cell.xa_ld ? cell.xa_ld : 384) + u0);
                         ho[0] = make_float4(hn[0], hn[1], hn[2], hn[3]); ho[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
                         if (cell.h_hi != nullptr) {          // fp16 hi / lo planes of h for the query GEMM
                             uint32_t hi[4], lo[4];
@@ -561,8 +561,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                 hi[i] = *reinterpret_cast<const uint32_t *>(&hh);
                                 lo[i] = *reinterpret_cast<const uint32_t *>(&ll);
                             }
-                            *reinterpret_cast<uint4 *>(cell.h_hi + R * 128 + u0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                            *reinterpret_cast<uint4 *>(cell.h_lo + R * 128 + u0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            const long long hl = cell.h_ld ? cell.h_ld : 128;
+                            *reinterpret_cast<uint4 *>(cell.h_hi + R * hl + u0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4 *>(cell.h_lo + R * hl + u0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                     continue;
