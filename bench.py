@@ -500,7 +500,21 @@ def other_configs(args, local_rank, tm):
         a = tm.run(lambda: bc.beam_search_prediction((rd, ed), beam, MAX_OUTPUT_LEN)[0], k, 1)
         d32["beam%d" % beam] = {"ms_per_step": a["ms"], "value": n32 / (a["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s"}
     out["depth_3_2"] = d32
-    del bc, rd, ed
+    del bc
+    # per-snippet early exit of the wave decoder: an end-token bias (as in tests/test_gpu_model.py::test_beam_early_termination)
+    # makes the beams of most snippets finish after a few steps, as trained weights do on real reads (mean 22 of 33 steps)
+    from ravvent_basecaller_b200 import weights as _w
+    ee = {"config": "joint model (2,1), beam 5, %d chunks, S=33; fc end-token bias +b" % n32}
+    for bias in (0.0, 1.0, 2.5):
+        w = _w.random_weights(22)
+        w["decoder/fc/bias"][1] += bias
+        bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "joint", 0., device=local_rank, precision=args.precision).load_weights(w)
+        a = tm.run(lambda: bc.beam_search_prediction((rd, ed), 5, MAX_OUTPUT_LEN)[0], k, 1, profile=True)
+        ee["bias_%g" % bias] = {"ms_per_step": a["ms"], "steps_executed": int(a["out"].shape[1]),
+                                "attention_ms": a["prof"]["attention"]["ms"] / k}
+        del bc
+    out["early_exit"] = ee
+    del rd, ed
     if not args.no_event_path:
         out["event_path"] = event_path_bench(local_rank)
         out["read_path"] = read_path_bench(local_rank, args.beam, args.precision)

@@ -45,10 +45,12 @@ __device__ __forceinline__ Row8 load_row8(const float *src) {
 // ---- masked softmax(values . q') . values, one warp per snippet (same scheme as decoder.cu phase 2b) ----------
 template <int WT>
 __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ values, const uint8_t *__restrict__ mask,
-                                                        const float *__restrict__ Q, float *__restrict__ xa, int B, int Tm, int W) {
+                                                        const float *__restrict__ Q, float *__restrict__ xa, int B, int Tm, int W,
+                                                        const int32_t *__restrict__ skip) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
+    if (skip[b]) return;          // every beam of this snippet has finished: fc_search emits the known continuation, nothing reads ctx
     const size_t bm = (size_t)b * Tm;
     unsigned mbits = 0;
 #pragma unroll
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
                                                         int32_t *first_done, float *scores, int32_t *step_ids, int32_t *parent_ids,
                                                         int B, int W, int S, int t, const float *__restrict__ xa, float *__restrict__ X,
                                                         uint16_t *__restrict__ x_hi, uint16_t *__restrict__ x_lo,
-                                                        const float *__restrict__ h0, uint16_t *__restrict__ x1_hi, uint16_t *__restrict__ x1_lo) {
+                                                        const float *__restrict__ h0, uint16_t *__restrict__ x1_hi, uint16_t *__restrict__ x1_lo,
+                                                        int32_t *__restrict__ skip) {
     __shared__ float a_s[4][WMAX * UNITS];
     __shared__ float lg_s[4][WMAX * 8];
     __shared__ float wfc_s[UNITS * VOCAB];
@@ -173,10 +176,21 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     for (int i = threadIdx.x; i < UNITS * VOCAB; i += blockDim.x) wfc_s[i] = wfc[i];
     const int b = blockIdx.x * 4 + wid;
     const bool active = b < B;
-    if (active)
+    const bool skipped = active && skip[b] != 0;
+    if (active && !skipped)
         for (int i = lane; i < W * UNITS; i += 32) a_s[wid][i] = att[(size_t)b * W * UNITS + i];
     __syncthreads();
     if (!active) return;
+    if (skipped) {
+        // All W beams finished with finite scores: every candidate other than (beam k, end token) costs dtype.min, so tfa's
+        // step selects exactly (k, end) for k = 0..W-1 in slot order (scores are already sorted): end token, identity
+        // parents, unchanged scores, lengths and flags.  The state rows of this snippet are never read again.
+        if (lane < W) {
+            const size_t o = ((size_t)b * S + t) * W + lane;
+            scores[o] = lp[(size_t)b * W + lane]; step_ids[o] = TOKEN_END; parent_ids[o] = lane;
+        }
+        return;
+    }
     for (int i = lane; i < W * VOCAB; i += 32) {
         const int k = i / VOCAB, v = i % VOCAB;
         float a = bfc[v];
@@ -233,6 +247,10 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     }
     const unsigned allfin = __ballot_sync(0xffffffffu, lane >= W || nfin);
     if (lane == 0 && allfin == 0xffffffffu && first_done[b] == S) first_done[b] = t;
+    // from the next step on this snippet is skipped -- only when the continuation is exactly known (finite scores; a
+    // -inf slot, possible for widths > 7, would let dtype.min candidates of other beams in)
+    const unsigned allfinite = __ballot_sync(0xffffffffu, lane >= W || sel_v > F32_MIN);
+    if (lane == 0 && allfin == 0xffffffffu && allfinite == 0xffffffffu) skip[b] = 1;
     // input of the next step's cell GEMM, gathered through the parents chosen just now: X[r] = [attention[src] | h[src]]
     // (two stacked cells: h of cell 0 comes from h0, and the top cell's h goes into the second half of X1[r] = [h0_new[r] | h1[src]])
     for (int k = 0; k < W; ++k) {
@@ -260,14 +278,14 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
 }
 
 __global__ void init_state_kernel(float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent, int32_t *first_done,
-                                  long long rows, int W, int S) {
+                                  int32_t *skip, long long rows, int W, int S) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const int k = (int)(r % W);
     lp[r] = (k == 0) ? 0.0f : -INFINITY;
     fin[r] = (k == 0) ? 0 : 1;
     len[r] = 0; tok[r] = TOKEN_START; parent[r] = k;
-    if (k == 0) first_done[r / W] = S;
+    if (k == 0) { first_done[r / W] = S; skip[r / W] = 0; }
 }
 
 // gather_tree on [B,S,W] arrays + T = max over snippets of (first all-finished step + 1)
@@ -296,9 +314,9 @@ __global__ void finalize_kernel(const int32_t *step_ids, const int32_t *parent_i
 }
 
 size_t workspace_floats(long long rows, int depth) {
-    // X 256 | Z 512 | XA 384 | Q 256 | ATT 128 | c x2 256 | lp 1  + ints: fin len tok parent 4 + first_done
+    // X 256 | Z 512 | XA 384 | Q 256 | ATT 128 | c x2 256 | lp 1  + ints: fin len tok parent 4 + first_done + skip
     // depth 2 adds: X1 planes 256 | H0 128 | c of cell 1 x2 256
-    return (size_t)rows * (256 + 512 + 384 + 256 + 128 + 256 + 1 + 4 + 1 + (depth == 2 ? 256 + 128 + 256 : 0)) + 64 + 64;
+    return (size_t)rows * (256 + 512 + 384 + 256 + 128 + 256 + 1 + 4 + 2 + (depth == 2 ? 256 + 128 + 256 : 0)) + 64 + 64;
 }
 
 int run(const Params &p, cudaStream_t s) {
@@ -309,9 +327,10 @@ int run(const Params &p, cudaStream_t s) {
     float *c0 = ATT + rows * 128, *c1 = c0 + rows * 128, *lp = c1 + rows * 128;
     int32_t *fin = reinterpret_cast<int32_t *>(lp + rows), *len = fin + rows, *tok = len + rows, *parent = tok + rows;
     int32_t *first_done = parent + rows;
+    int32_t *skip = first_done + rows;        // per snippet: all beams finished, continuation known (see fc_search)
     const bool two = p.depth == 2;
     // depth 2 only; re-aligned to 256 bytes (the scalar arrays before it leave any 4-byte offset): TMA source + vector stores
-    float *X1 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(first_done + rows) + 255) & ~uintptr_t(255));
+    float *X1 = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(skip + rows) + 255) & ~uintptr_t(255));
     float *H0 = X1 + rows * 256, *d0 = H0 + rows * 128, *d1 = d0 + rows * 128;
     uint16_t *x1_hi = reinterpret_cast<uint16_t *>(X1), *x1_lo = x1_hi + rows * 256;
     // fp16-plane operands share the X / Z regions: X = [hi plane | lo plane] of [rows][256] halves, Z holds the h planes
@@ -333,7 +352,7 @@ int run(const Params &p, cudaStream_t s) {
     // profiling (bench.py): the attention kernel is timed per launch as its own kind, everything else as "decoder"
     {
         ProfScope ps(KK_DECODER, s);
-        init_state_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(lp, fin, len, tok, parent, first_done, rows, p.W, p.S);
+        init_state_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(lp, fin, len, tok, parent, first_done, skip, rows, p.W, p.S);
         RVB_LAUNCH_CHECK();
     }
     int nl = 1;
@@ -364,16 +383,16 @@ int run(const Params &p, cudaStream_t s) {
         }
         {
             ProfScope ps(KK_ATTENTION, s);
-            if (p.W == 1) attention_kernel<1><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W);
-            else if (p.W <= 5) attention_kernel<5><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W);
-            else attention_kernel<9><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W);
+            if (p.W == 1) attention_kernel<1><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+            else if (p.W <= 5) attention_kernel<5><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+            else attention_kernel<9><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
         }
         {
             ProfScope ps(KK_DECODER, s);
             RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
                                                 p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr,
-                                                two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr);
+                                                two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr, skip);
             RVB_LAUNCH_CHECK();
         }
         nl += 2;

@@ -117,7 +117,7 @@ def test_beam_matches_oracle(kind, W):
     assert ties == 0 or ties <= 2
 
 
-@pytest.mark.parametrize("W", [1, 5])
+@pytest.mark.parametrize("W", [1, 5, 9])
 def test_beam_early_termination_matches_oracle(W):
     """A large end-token bias makes every beam finish within a few steps: the kernel's early exit must
     reproduce what tfa's dynamic_decode would have produced (T, ids, scores), also when other
@@ -132,6 +132,11 @@ def test_beam_early_termination_matches_oracle(W):
     rid, _ = mr.beam_search(w, enc, mask, W, L)
     assert rid.shape[1] < L - 1, "the bias should end decoding early"
     check_beam(got, w, enc, mask, W, L, label=f" early-stop W={W}")
+    # a milder bias: some snippets finish (and are skipped by the attention kernel from then on) while others decode on
+    b2 = W22["decoder/fc/bias"].copy(); b2[mr.TOKEN_END] += 1.0
+    w["decoder/fc/bias"] = b2
+    got = make("joint", weights=w).beam_search_prediction(x, W, 34, return_all_beams=True)
+    check_beam(got, w, enc, mask, W, 34, label=f" mixed early-stop W={W}")
 
 
 @pytest.mark.parametrize("enc_depth,W", [(3, 1), (3, 5), (2, 5)])
