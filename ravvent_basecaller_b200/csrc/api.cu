@@ -537,9 +537,9 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
-        // Wave-level decoder for every beam width in parity mode; in reduced-precision mode width 1 stays on the persistent
-        // kernel, which streams the fp16 copy of the memory (half the bytes).  Greedy search keeps the persistent kernel.
-        if (beam && m->dec_wave && (W >= 2 || m->precision == RVB_PREC_FP32)) {
+        // Wave-level decoder for every beam width (reduced-precision mode: its attention kernel streams the fp16 copy of the
+        // memory).  Greedy search keeps the persistent kernel.
+        if (beam && m->dec_wave) {
             const size_t rows = (size_t)m->wave * W;
             if (rows > m->dw_ws_rows) {
                 dfree(m, m->dw_ws);
@@ -548,6 +548,9 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             }
             decw::Params q{};
             q.values = m->enc_out; q.mask = m->mask;
+            // fp16 copy of the memory: only at width 1, where the attention kernel is bandwidth bound (measured: at width 5 it is
+            // issue bound and the widening conversions cost more than the halved bytes save, 199 -> 251 ms per step)
+            q.values16 = (m->precision == RVB_PREC_BF16 && W == 1) ? m->enc_out16 : nullptr;
             q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
             q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];
             q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;

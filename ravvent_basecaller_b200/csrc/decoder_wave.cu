@@ -42,9 +42,21 @@ __device__ __forceinline__ Row8 load_row8(const float *src) {
     return r;
 }
 
+// fp16 memory rows (reduced-precision mode: half the decode-time HBM bytes), widened to fp32 in registers
+__device__ __forceinline__ Row8 load_row8(const __half *src) {
+    const uint2 a = __ldg(reinterpret_cast<const uint2 *>(src)), c = __ldg(reinterpret_cast<const uint2 *>(src + UNITS));
+    auto widen = [](uint32_t v) -> f32x2 {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&v));
+        return pack2(f.x, f.y);
+    };
+    Row8 r;
+    r.p[0] = widen(a.x); r.p[1] = widen(a.y); r.p[2] = widen(c.x); r.p[3] = widen(c.y);
+    return r;
+}
+
 // ---- masked softmax(values . q') . values, one warp per snippet (same scheme as decoder.cu phase 2b) ----------
-template <int WT>
-__global__ void __launch_bounds__(128) attention_kernel(const float *__restrict__ values, const uint8_t *__restrict__ mask,
+template <int WT, typename VT>
+__global__ void __launch_bounds__(128) attention_kernel(const VT *__restrict__ values, const uint8_t *__restrict__ mask,
                                                         const float *__restrict__ Q, float *__restrict__ xa, int B, int Tm, int W,
                                                         const int32_t *__restrict__ skip) {
     const int lane = threadIdx.x & 31;
@@ -71,7 +83,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float *__restrict_
             for (int e = 0; e < 4; ++e) q[w][e] = r.p[e];
         }
     }
-    const float *vbase = values + bm * ENC_OUT + 4 * lane;
+    const VT *vbase = values + bm * ENC_OUT + 4 * lane;
     Row8 cur[4], nxt[4];
     unsigned vb_cur = __shfl_sync(0xffffffffu, mbits, 0) & 0xFu, vb_nxt = 0;
 #pragma unroll
@@ -383,9 +395,14 @@ int run(const Params &p, cudaStream_t s) {
         }
         {
             ProfScope ps(KK_ATTENTION, s);
-            if (p.W == 1) attention_kernel<1><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-            else if (p.W <= 5) attention_kernel<5><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-            else attention_kernel<9><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+            if (p.values16 != nullptr) {           // reduced-precision mode: fp16 copy of the memory
+                const __half *v16 = reinterpret_cast<const __half *>(p.values16);
+                if (p.W == 1) attention_kernel<1, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+                else if (p.W <= 5) attention_kernel<5, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+                else attention_kernel<9, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+            } else if (p.W == 1) attention_kernel<1, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+            else if (p.W <= 5) attention_kernel<5, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+            else attention_kernel<9, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
         }
         {
             ProfScope ps(KK_DECODER, s);

@@ -100,6 +100,7 @@ int run(const Params &p, cudaStream_t stream);
 namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >= 2), decoder_wave.cu
 struct Params {
     const float *values;        // [B,Tm,256]
+    const uint16_t *values16;   // optional fp16 copy of values (reduced-precision mode): the attention kernel streams it instead
     const uint8_t *mask;        // [B,Tm]
     const float *wg_hiT, *wg_loT;   // tf32 hi / lo of [att-input rows ; recurrent kernel], transposed [512,256], [unit][gate] columns
     const float *wm_hiT, *wm_loT;   // W_mem^T as a [K=128, N=256] weight, transposed [256,128]
