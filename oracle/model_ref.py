@@ -56,25 +56,38 @@ def _lstm_weights(rng, n_in, units):
             "bias": b}
 
 
+def _gru_weights(rng, n_in, units):
+    """Keras GRUCell defaults (reset_after=True): kernel [in,3u], recurrent_kernel [u,3u], bias [2,3u] = (input, recurrent),
+    gate blocks z, r, h."""
+    return {"kernel": _glorot(rng, n_in, 3 * units),
+            "recurrent_kernel": _orthogonal(rng, units, 3 * units),
+            "bias": np.zeros((2, 3 * units), dtype=np.float32)}
+
+
 def init_weights(seed=22, enc_units=128, dec_units=128, encoder_depth=2, decoder_depth=1,
-                 vocab_size=7, random_bias=False):
+                 vocab_size=7, random_bias=False, rnn_type="bilstm"):
     """Flat dict name -> float32 array (the .npz interchange layout of
     Basecaller.load_weights).  ``random_bias`` perturbs biases so tests see a
-    non-trivial bias path."""
+    non-trivial bias path.  rnn_type in {'bilstm', 'lstm', 'bigru', 'gru'} as in basecaller.py:25-46, 86-89:
+    'bi' -> Bidirectional encoders (forward + backward weights, 2*enc_units outputs), otherwise forward only;
+    'lstm' / 'gru' picks the cell of the encoders AND of the decoder (basecaller.py:195 strips the 'bi')."""
     rng = np.random.default_rng(seed)
     w = {}
+    bi = "bi" in rnn_type
+    cell_w = _lstm_weights if "lstm" in rnn_type else _gru_weights
+    enc_out = (2 if bi else 1) * enc_units
     for enc, feat in (("encoder_raw", 1), ("encoder_event", 5)):
         for l in range(encoder_depth):
-            n_in = feat if l == 0 else 2 * enc_units
-            for d in ("forward", "backward"):
-                for k, v in _lstm_weights(rng, n_in, enc_units).items():
+            n_in = feat if l == 0 else enc_out
+            for d in (("forward", "backward") if bi else ("forward",)):
+                for k, v in cell_w(rng, n_in, enc_units).items():
                     w[f"{enc}/layer{l}/{d}/{k}"] = v
     for j in range(decoder_depth):
         n_in = vocab_size + dec_units if j == 0 else dec_units
-        for k, v in _lstm_weights(rng, n_in, dec_units).items():
+        for k, v in cell_w(rng, n_in, dec_units).items():
             w[f"decoder/cell{j}/{k}"] = v
-    w["decoder/memory_layer/kernel"] = _glorot(rng, 2 * enc_units, dec_units)
-    w["decoder/attention_layer/kernel"] = _glorot(rng, dec_units + 2 * enc_units, dec_units)
+    w["decoder/memory_layer/kernel"] = _glorot(rng, enc_out, dec_units)
+    w["decoder/attention_layer/kernel"] = _glorot(rng, dec_units + enc_out, dec_units)
     w["decoder/fc/kernel"] = _glorot(rng, dec_units, vocab_size)
     w["decoder/fc/bias"] = np.zeros(vocab_size, dtype=np.float32)
     if random_bias:
@@ -101,15 +114,35 @@ def lstm_cell(x, h, c, kernel, recurrent_kernel, bias):
     return h2, c2
 
 
+def gru_cell(x, h, kernel, recurrent_kernel, bias):
+    """Keras GRUCell step, reset_after=True (the TF2 default; [Keras-recall], same formula as torch.nn.GRUCell):
+    gate blocks z, r, h; the reset gate multiplies the recurrent part INCLUDING its bias."""
+    u = h.shape[-1]
+    mx = x @ kernel + bias[0]
+    mh = h @ recurrent_kernel + bias[1]
+    z = sigmoid(mx[:, :u] + mh[:, :u])
+    r = sigmoid(mx[:, u:2 * u] + mh[:, u:2 * u])
+    hh = np.tanh(mx[:, 2 * u:] + r * mh[:, 2 * u:])
+    return z * h + (1.0 - z) * hh
+
+
+def rnn_cell(x, h, c, kernel, recurrent_kernel, bias):
+    """LSTMCell or GRUCell by the shape of the bias ([4u] vs [2,3u]); a GRU's state is h alone (c mirrors it)."""
+    if bias.ndim == 2:
+        h2 = gru_cell(x, h, kernel, recurrent_kernel, bias)
+        return h2, h2
+    return lstm_cell(x, h, c, kernel, recurrent_kernel, bias)
+
+
 def rnn_direction(x, cell_w, h0, c0, reverse):
-    """One Keras RNN(LSTMCell, return_sequences, return_state), optionally
+    """One Keras RNN(cell, return_sequences, return_state), optionally
     go_backwards with the output re-reversed as Bidirectional does (A.2)."""
     B, T, _ = x.shape
     h, c = h0, c0
     ys = np.empty((B, T, h0.shape[-1]), dtype=x.dtype)
     order = range(T - 1, -1, -1) if reverse else range(T)
     for t in order:
-        h, c = lstm_cell(x[:, t], h, c, cell_w["kernel"], cell_w["recurrent_kernel"], cell_w["bias"])
+        h, c = rnn_cell(x[:, t], h, c, cell_w["kernel"], cell_w["recurrent_kernel"], cell_w["bias"])
         ys[:, t] = h
     return ys, h, c
 
@@ -127,8 +160,11 @@ def encoder(x, w, prefix, depth, units):
     out = x
     for l in range(depth):
         fw = {k: w[f"{prefix}/layer{l}/forward/{k}"] for k in ("kernel", "recurrent_kernel", "bias")}
-        bw = {k: w[f"{prefix}/layer{l}/backward/{k}"] for k in ("kernel", "recurrent_kernel", "bias")}
         yf, hf, cf = rnn_direction(out, fw, states[0], states[1], reverse=False)
+        if f"{prefix}/layer{l}/backward/kernel" not in w:          # unidirectional: RNN(cell) without Bidirectional
+            out, states = yf, [hf, cf, states[2], states[3]]
+            continue
+        bw = {k: w[f"{prefix}/layer{l}/backward/{k}"] for k in ("kernel", "recurrent_kernel", "bias")}
         yb, hb, cb = rnn_direction(out, bw, states[2], states[3], reverse=True)
         out = np.concatenate([yf, yb], axis=-1)
         states = [hf, cf, hb, cb]
@@ -201,8 +237,8 @@ def decoder_step(w, tokens, state, keys, values, mask, decoder_depth, vocab_size
     new_cells = []
     for j in range(decoder_depth):
         h, c = state.cells[j]
-        h2, c2 = lstm_cell(x, h, c, w[f"decoder/cell{j}/kernel"], w[f"decoder/cell{j}/recurrent_kernel"],
-                           w[f"decoder/cell{j}/bias"])
+        h2, c2 = rnn_cell(x, h, c, w[f"decoder/cell{j}/kernel"], w[f"decoder/cell{j}/recurrent_kernel"],
+                          w[f"decoder/cell{j}/bias"])
         new_cells.append((h2, c2))
         x = h2
     query = x

@@ -32,13 +32,23 @@ class TorchDecoder(torch.nn.Module):
         self.u, self.vocab, self.dt = u, vocab, dtype
         self.cells = torch.nn.ModuleList()
         for j in range(decoder_depth):
-            k = w[f"decoder/cell{j}/kernel"]
-            cell = torch.nn.LSTMCell(k.shape[0], u, dtype=dtype)          # gate order i, f, g, o == Keras i, f, c, o
-            with torch.no_grad():
-                cell.weight_ih.copy_(torch.as_tensor(k.T.copy(), dtype=dtype))
-                cell.weight_hh.copy_(torch.as_tensor(w[f"decoder/cell{j}/recurrent_kernel"].T.copy(), dtype=dtype))
-                cell.bias_ih.copy_(torch.as_tensor(w[f"decoder/cell{j}/bias"], dtype=dtype))
-                cell.bias_hh.zero_()
+            k, rk, bias = (w[f"decoder/cell{j}/{n}"] for n in ("kernel", "recurrent_kernel", "bias"))
+            if bias.ndim == 2:
+                # Keras GRUCell(reset_after=True) == torch.nn.GRUCell with the gate blocks reordered: Keras z, r, h -> torch r, z, n
+                cell = torch.nn.GRUCell(k.shape[0], u, dtype=dtype)
+                perm = np.concatenate([np.arange(u, 2 * u), np.arange(0, u), np.arange(2 * u, 3 * u)])
+                with torch.no_grad():
+                    cell.weight_ih.copy_(torch.as_tensor(k.T[perm].copy(), dtype=dtype))
+                    cell.weight_hh.copy_(torch.as_tensor(rk.T[perm].copy(), dtype=dtype))
+                    cell.bias_ih.copy_(torch.as_tensor(bias[0][perm].copy(), dtype=dtype))
+                    cell.bias_hh.copy_(torch.as_tensor(bias[1][perm].copy(), dtype=dtype))
+            else:
+                cell = torch.nn.LSTMCell(k.shape[0], u, dtype=dtype)      # gate order i, f, g, o == Keras i, f, c, o
+                with torch.no_grad():
+                    cell.weight_ih.copy_(torch.as_tensor(k.T.copy(), dtype=dtype))
+                    cell.weight_hh.copy_(torch.as_tensor(rk.T.copy(), dtype=dtype))
+                    cell.bias_ih.copy_(torch.as_tensor(bias, dtype=dtype))
+                    cell.bias_hh.zero_()
             self.cells.append(cell)
 
         def dense(name, bias=None):
@@ -73,7 +83,11 @@ class TorchDecoder(torch.nn.Module):
         x = torch.cat([torch.nn.functional.one_hot(tokens.long(), self.vocab).to(self.dt), state["attention"]], dim=1)
         cells = []
         for cell, (h, c) in zip(self.cells, state["cells"]):
-            h, c = cell(x, (h, c))
+            if isinstance(cell, torch.nn.GRUCell):
+                h = cell(x, h)
+                c = h
+            else:
+                h, c = cell(x, (h, c))
             cells.append((h, c))
             x = h
         score = torch.bmm(self.keys, x.unsqueeze(2)).squeeze(2)

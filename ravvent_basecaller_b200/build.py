@@ -29,6 +29,7 @@ SOURCES = {
     "proj_gemm.cu": [],
     "decoder.cu": [],
     "decoder_wave.cu": [],
+    "attention_tc.cu": [],
     "snippets.cu": ["-fmad=false"],
     "merger.cu": ["-fmad=false"],        # float64 alignment scores are compared exactly: no a*b+c contraction
 }

@@ -81,6 +81,8 @@ struct rvb_model {
     float *st[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [encoder][ping-pong]
     float *enc_out = nullptr, *keys = nullptr;
     uint16_t *enc_out16 = nullptr;             // fp16 copy of enc_out (reduced-precision mode only)
+    uint16_t *enc_hi = nullptr, *enc_lo = nullptr;   // fp16 hi / lo planes of the memory (tcgen05 attention, beam widths >= 2)
+    bool att_tc = false;
     uint8_t *mask = nullptr;
     int32_t *step_ids = nullptr, *parent_ids = nullptr;
     // host-buffer variant: double-buffered I/O sets, pinned staging, copy streams (HostPipe, below)
@@ -152,6 +154,8 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     m->rec_tc = m->use_tc && !(r && strcmp(r, "ffma") == 0);
     const char *dv = getenv("RVB_DECODER");
     m->dec_wave = m->use_tc && !(dv && strcmp(dv, "persistent") == 0);
+    const char *av = getenv("RVB_ATT");
+    m->att_tc = m->dec_wave && m->rec_tc && !(av && strcmp(av, "ffma") == 0);
     *out = m;
     return RVB_OK;
 }
@@ -413,6 +417,11 @@ static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
         RVB_CHECK(dmalloc(m, &m->enc_out, wv * Tm * ENC_OUT));
         if (m->precision == RVB_PREC_BF16 && m->rec_tc) { dfree(m, m->enc_out16); RVB_CHECK(dmalloc(m, &m->enc_out16, wv * Tm * ENC_OUT)); }
         RVB_CHECK(dmalloc(m, &m->mask, wv * Tm));
+        if (m->att_tc) {
+            dfree(m, m->enc_hi); dfree(m, m->enc_lo);
+            RVB_CHECK(dmalloc(m, &m->enc_hi, wv * Tm * ENC_OUT));
+            RVB_CHECK(dmalloc(m, &m->enc_lo, wv * Tm * ENC_OUT));
+        }
         m->ws_tm = Tm;
     }
     if ((size_t)S * W > m->ws_sw) {
@@ -426,7 +435,8 @@ static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
 
 // One encoder (raw: e = 0, event: e = 1) over nb snippets; final layer writes into
 // out[b, t_off + t, :] with row stride Tm*256 (basecaller.py:48-59, 405).
-static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, float *out, int Tm, int t_off, cudaStream_t s) {
+// planes: the final layer writes the memory as fp16 hi / lo planes (m->enc_hi / enc_lo, [nb,Tm,256]) instead of fp32 `out`.
+static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, float *out, int Tm, int t_off, cudaStream_t s, bool planes = false) {
     const int feat = e == 0 ? 1 : 5;
     float **yb = e == 0 ? m->y_raw : m->y_ev;
     float *G = e == 0 ? m->G_raw : m->G_ev;
@@ -443,10 +453,14 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
         // intermediate layers hand their output to K2 as fp16 hi/lo planes (time-major, same bytes as fp32)
         uint16_t *pl_hi = reinterpret_cast<uint16_t *>(yb[l & 1]);
         uint16_t *pl_lo = pl_hi + (size_t)nbp * T * ENC_OUT;
-        p.y = last ? out + (size_t)t_off * ENC_OUT : nullptr;
+        p.y = (last && !planes) ? out + (size_t)t_off * ENC_OUT : nullptr;
         p.y_bs = (long long)Tm * ENC_OUT; p.y_ts = ENC_OUT;
         p.y16_hi = last ? nullptr : pl_hi; p.y16_lo = last ? nullptr : pl_lo;
         p.y16_bs = ENC_OUT; p.y16_ts = nbp * ENC_OUT;
+        if (last && planes) {       // batch-major planes of the attention memory
+            p.y16_hi = m->enc_hi + (size_t)t_off * ENC_OUT; p.y16_lo = m->enc_lo + (size_t)t_off * ENC_OUT;
+            p.y16_bs = (long long)Tm * ENC_OUT; p.y16_ts = ENC_OUT;
+        }
         p.yv16 = (last && m->enc_out16 != nullptr && out == m->enc_out) ? m->enc_out16 + (size_t)t_off * ENC_OUT : nullptr;
         p.B = nb; p.T = T; p.abort_flag = m->d_abort; p.precision = m->precision;
         if (l > 0) {
@@ -489,10 +503,10 @@ static int check_inputs(rvb_model *m, const float *raw, int t_raw, const float *
 }
 
 // encoders + mask + keys for one wave, into the handle's workspace
-static int encode_wave(rvb_model *m, const float *raw, int t_raw, const float *ev, int t_ev, int nb, int Tm, cudaStream_t s) {
+static int encode_wave(rvb_model *m, const float *raw, int t_raw, const float *ev, int t_ev, int nb, int Tm, cudaStream_t s, bool planes = false) {
     const bool need_raw = m->input_kind != RVB_INPUT_EVENT, need_ev = m->input_kind != RVB_INPUT_RAW;
-    if (need_raw) RVB_CHECK(encode_branch(m, 0, raw, t_raw, nb, m->enc_out, Tm, 0, s));
-    if (need_ev) RVB_CHECK(encode_branch(m, 1, ev, t_ev, nb, m->enc_out, Tm, need_raw ? t_raw : 0, s));
+    if (need_raw) RVB_CHECK(encode_branch(m, 0, raw, t_raw, nb, m->enc_out, Tm, 0, s, planes));
+    if (need_ev) RVB_CHECK(encode_branch(m, 1, ev, t_ev, nb, m->enc_out, Tm, need_raw ? t_raw : 0, s, planes));
     return RVB_OK;
 }
 
@@ -535,8 +549,11 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
     RVB_CHECK(ensure_workspace(m, t_raw, t_event, S, W));
     for (int64_t b0 = 0; b0 < batch; b0 += m->wave) {
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
+        // beam widths >= 2: the attention runs on tcgen05 and reads the memory as fp16 hi / lo planes, which the last encoder
+        // layer then writes INSTEAD of the fp32 rows (same bytes)
+        const bool tc_att = beam && m->dec_wave && m->att_tc && W >= 2;
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
-                              need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s));
+                              need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s, tc_att));
         // Wave-level decoder for every beam width (reduced-precision mode: its attention kernel streams the fp16 copy of the
         // memory).  Greedy search keeps the persistent kernel.
         if (beam && m->dec_wave) {
@@ -551,6 +568,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             // fp16 copy of the memory: only at width 1, where the attention kernel is bandwidth bound (measured: at width 5 it is
             // issue bound and the widening conversions cost more than the halved bytes save, 199 -> 251 ms per step)
             q.values16 = (m->precision == RVB_PREC_BF16 && W == 1) ? m->enc_out16 : nullptr;
+            q.v_hi = tc_att ? m->enc_hi : nullptr; q.v_lo = tc_att ? m->enc_lo : nullptr;
             q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
             q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];
             q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;

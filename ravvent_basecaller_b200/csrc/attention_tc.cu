@@ -1,0 +1,382 @@
+// K4 attention on the 5th-generation tensor cores, for beam widths >= 2 (decoder_wave.cu keeps the FFMA kernel for width 1,
+// which is HBM bound there).
+//
+// Replaces, per decode step, tfa LuongAttention + the context reduction of AttentionWrapper (reference basecaller.py:117-134,
+// SURVEY A.3 / A.3b) for all beams of a snippet at once:
+//     S[t, w]  = V[t, :] . q'[w, :]                 (q' = W_mem h: the memory layer is folded into the query)
+//     P[t, w]  = softmax over the unmasked rows t
+//     ctx[w,:] = sum_t P[t, w] V[t, :]
+// The FFMA form of this (one warp per snippet, columns split over the lanes) needs a 5-stage shuffle butterfly per
+// (row, beam) score and is instruction bound at beam 5 (47 % of the HBM rate).  Here both contractions run on tcgen05:
+//   * the memory V is kept by K3 as fp16 hi + lo planes ([B, Tm, 256] each, the same bytes as fp32) and TMA-loaded in
+//     128-row tiles, cut into "units" of 64 KB = 128 rows x 128 columns x (hi, lo) -- a ring of three units;
+//   * scores: D_s[128 rows, 16] += V_unit (A operand, K-major: K = columns) . Q^T (B operand: beams padded to N = 16),
+//     3 split passes (V_lo.Q_hi + V_hi.Q_lo + V_hi.Q_hi) -> fp32-level accuracy on the fp16 pipe;
+//   * context: D_c[128 columns, 16] += V_unit^T (the SAME shared-memory bytes read as an MN-major A operand: M = columns,
+//     K = rows) . P (B operand written by the softmax warps as fp16 hi / lo), again 3 passes;
+//   * four softmax warps own the 128 TMEM lanes: online softmax over the (at most two) row tiles, rescaling the context
+//     accumulator in TMEM (tcgen05.ld / st) between them, normalising at the end.
+// One persistent CTA per SM walks its snippets; warp roles: w0 TMA producer, w1 TMEM allocation + MMA issue, w2..w5 softmax.
+// Every mbarrier wait is bounded (abort flag), as in the projection kernel.
+#include "proj_gemm_tc.cuh"
+
+namespace rvb {
+namespace atc {
+
+using gemm::tc::make_desc;
+using gemm::tc::make_idesc_f16;
+using gemm::tc::mbar_arrive;
+using gemm::tc::mbar_expect_tx;
+using gemm::tc::mbar_init;
+using gemm::tc::mbar_wait;
+using gemm::tc::smem_u32;
+using gemm::tc::umma_commit;
+using gemm::tc::umma_f16;
+
+constexpr int ROWS = 128;                       // memory rows per tile = TMEM lanes
+constexpr int NB = 16;                          // beams padded to the smallest MMA N at M = 128
+constexpr int BOX_BYTES = ROWS * 128;           // [128 rows][64 fp16], 128-byte swizzle
+constexpr int UNIT_BYTES = 4 * BOX_BYTES;       // hi cols a | hi cols b | lo cols a | lo cols b  (128 columns of both planes)
+constexpr int RING = 3;
+constexpr int QBOX = NB * 128;                  // [16 beams][64 fp16]
+constexpr int Q_BYTES = 2 * 4 * QBOX;           // (hi | lo) x 4 K-boxes of 64 columns
+constexpr int P_BYTES = 2 * 2 * QBOX;           // (hi | lo) x 2 K-boxes of 64 rows
+constexpr int THREADS = 192;
+constexpr size_t SMEM = 1024 + (size_t)RING * UNIT_BYTES + Q_BYTES + P_BYTES + 1024;
+constexpr int TMEM_COLS = 64;                   // scores 2 x 16 | context 2 x 16
+constexpr int WMAX_ = 9;                        // widest beam (decoder_wave.cu WMAX)
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// MN-major, SWIZZLE_128B matrix descriptor: 64 M-elements (128 bytes) are contiguous, the next 64 are LBO bytes further,
+// K advances by 128 bytes per element inside an 8-row swizzle atom and by SBO bytes per atom.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        :: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
+__device__ __forceinline__ void split_f16(float v, uint16_t &hi, uint16_t &lo) {
+    const __half h = __float2half_rn(v);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+}
+// byte offset of element (row n, k) inside a K-major SWIZZLE_128B box of [rows][64 fp16]
+__device__ __forceinline__ uint32_t kmajor_off(int n, int k) {
+    return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                    const uint8_t *__restrict__ mask, const float *__restrict__ Q, float *__restrict__ xa,
+                    const int32_t *__restrict__ skip, int B, int Tm, int W, int *abort_flag) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char *ring = smem;
+    unsigned char *qbuf = smem + (size_t)RING * UNIT_BYTES;
+    unsigned char *pbuf = qbuf + Q_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(pbuf + P_BYTES);
+    uint64_t *full = bars, *empty = bars + RING;
+    uint64_t *q_ready = bars + 2 * RING, *p_ready = q_ready + 1, *c_done = q_ready + 2, *s_ready = q_ready + 3;   // s_ready[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_ready + 2);
+    float *red = reinterpret_cast<float *>(tmem_slot + 2);          // [2 buffers][4 warps][16]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (Tm + ROWS - 1) / ROWS;                     // 1 or 2 (Tm <= 256)
+
+    if (threadIdx.x == 0) {
+        for (int u = 0; u < RING; ++u) { mbar_init(&full[u], 1); mbar_init(&empty[u], 1); }
+        mbar_init(q_ready, 128); mbar_init(p_ready, 128); mbar_init(c_done, 1);
+        mbar_init(&s_ready[0], 1); mbar_init(&s_ready[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // beams W..15 of the B operands are zero for the whole kernel
+    for (int i = threadIdx.x; i < (Q_BYTES + P_BYTES) / 16; i += THREADS) reinterpret_cast<uint4 *>(qbuf)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: units (tile, column half) in order =====================
+        if (lane == 0) {
+            uint32_t n = 0;                                         // units issued so far
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                if (skip[b]) continue;
+                for (int t = 0; t < n_tiles; ++t)
+                    for (int h = 0; h < 2; ++h, ++n) {
+                        const uint32_t u = n % RING, round = n / RING;
+                        if (round > 0 && !mbar_wait(&empty[u], (round - 1) & 1, abort_flag)) return;
+                        unsigned char *dst = ring + (size_t)u * UNIT_BYTES;
+                        mbar_expect_tx(&full[u], UNIT_BYTES);
+                        tma_load_3d(&map_hi, &full[u], dst, 128 * h, ROWS * t, b);
+                        tma_load_3d(&map_hi, &full[u], dst + BOX_BYTES, 128 * h + 64, ROWS * t, b);
+                        tma_load_3d(&map_lo, &full[u], dst + 2 * BOX_BYTES, 128 * h, ROWS * t, b);
+                        tma_load_3d(&map_lo, &full[u], dst + 3 * BOX_BYTES, 128 * h + 64, ROWS * t, b);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_f16(ROWS, NB);                   // A, B K-major
+            constexpr uint32_t idesc_c = make_idesc_f16(ROWS, NB) | (1u << 15);      // A MN-major (V^T), B K-major
+            const uint32_t q0 = smem_u32(qbuf), p0 = smem_u32(pbuf), r0 = smem_u32(ring);
+            uint32_t n = 0, nq = 0, np = 0;                           // units consumed, q_ready / p_ready phases seen
+            // scores of unit (t, h): 128 columns of K = 2 boxes x 4 k-steps, 3 split passes
+            auto scores_unit = [&](uint32_t ubase, int t, int h) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const int pa = (pass == 0) ? 1 : 0, pb = (pass == 1) ? 1 : 0;       // V_lo.Q_hi, V_hi.Q_lo, V_hi.Q_hi
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t ad = make_desc(ubase + (pa * 2 + jj) * BOX_BYTES + ks * 32);
+                            const uint64_t bd = make_desc(q0 + pb * (4 * QBOX) + (2 * h + jj) * QBOX + ks * 32);
+                            umma_f16(tmem_base + 16u * (uint32_t)t, ad, bd, idesc_s, (h | pass | jj | ks) ? 1u : 0u);
+                        }
+                }
+            };
+            // context of unit (t, h): columns 128h..128h+127 (M), this tile's 128 rows (K = 8 k-steps of 16), 3 split passes
+            auto ctx_unit = [&](uint32_t ubase, int t, int h) {
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const int pa = (pass == 0) ? 1 : 0, pb = (pass == 1) ? 1 : 0;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint64_t ad = make_desc_mn(ubase + pa * 2 * BOX_BYTES + ks * 2048, BOX_BYTES, 1024);
+                        const uint64_t bd = make_desc(p0 + pb * (2 * QBOX) + (ks >> 2) * QBOX + (ks & 3) * 32);
+                        umma_f16(tmem_base + 32u + 16u * (uint32_t)h, ad, bd, idesc_c, (t | pass | ks) ? 1u : 0u);
+                    }
+                }
+            };
+            auto wait_unit = [&](uint32_t k) -> bool { return mbar_wait(&full[k % RING], (k / RING) & 1, abort_flag); };
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                if (skip[b]) continue;
+                if (!mbar_wait(q_ready, nq++ & 1, abort_flag)) return;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t nb0 = n;                              // first unit of this snippet
+                // scores of tile 0 (both column halves), then as much of tile 1 as the ring holds
+                for (int h = 0; h < 2; ++h) {
+                    if (!wait_unit(nb0 + h)) return;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    scores_unit(r0 + ((nb0 + h) % RING) * UNIT_BYTES, 0, h);
+                }
+                umma_commit(&s_ready[0]);
+                if (n_tiles == 2) {
+                    if (!wait_unit(nb0 + 2)) return;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    scores_unit(r0 + ((nb0 + 2) % RING) * UNIT_BYTES, 1, 0);
+                }
+                for (int t = 0; t < n_tiles; ++t) {
+                    if (!mbar_wait(p_ready, np++ & 1, abort_flag)) return;       // P of tile t written (and ctx rescaled)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t k = nb0 + 2 * t + h;
+                        ctx_unit(r0 + (k % RING) * UNIT_BYTES, t, h);
+                        umma_commit(&empty[k % RING]);                           // unit free when these MMAs retire
+                    }
+                    umma_commit(c_done);
+                    if (t == 0 && n_tiles == 2) {
+                        // second column half of tile 1 lands in a unit freed just now
+                        if (!wait_unit(nb0 + 3)) return;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        scores_unit(r0 + ((nb0 + 3) % RING) * UNIT_BYTES, 1, 1);
+                        umma_commit(&s_ready[1]);
+                    }
+                }
+                n += 2 * n_tiles;
+            }
+        }
+    } else {
+        // ===================== softmax warps: thread e <-> TMEM lane e =====================
+        const int qd = warp & 3;
+        const int e = 32 * qd + lane;                                // row inside a tile (scores) / column inside a half (context)
+        const uint32_t tlane = tmem_base + ((uint32_t)(32 * qd) << 16);
+        const uint32_t q0 = smem_u32(qbuf), p0 = smem_u32(pbuf);
+        uint32_t ns0 = 0, ns1 = 0, nc = 0, nred = 0;
+        auto reduce16 = [&](float (&v)[WMAX_], bool is_max) {        // all-reduce over the 128 softmax threads, per beam
+#pragma unroll
+            for (int w = 0; w < WMAX_; ++w)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float other = __shfl_xor_sync(0xffffffffu, v[w], o);
+                    v[w] = is_max ? fmaxf(v[w], other) : v[w] + other;
+                }
+            float *buf = red + (nred++ & 1) * 64;
+            if (lane == 0) {
+#pragma unroll
+                for (int w = 0; w < WMAX_; ++w) buf[(warp - 2) * 16 + w] = v[w];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int w = 0; w < WMAX_; ++w) {
+                const float a = buf[w], b2 = buf[16 + w], c2 = buf[32 + w], d2 = buf[48 + w];
+                v[w] = is_max ? fmaxf(fmaxf(a, b2), fmaxf(c2, d2)) : (a + b2) + (c2 + d2);
+            }
+        };
+        for (int b = blockIdx.x; b < B; b += gridDim.x) {
+            if (skip[b]) continue;
+            // ---- queries of this snippet -> fp16 hi / lo B tiles (the previous snippet's score MMAs have retired: s_ready seen)
+            for (int w = 0; w < W; ++w) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int k = e + 128 * half;
+                    uint16_t hi, lo;
+                    split_f16(__ldg(Q + ((size_t)b * W + w) * ENC_OUT + k), hi, lo);
+                    const uint32_t off = (uint32_t)(k >> 6) * QBOX + kmajor_off(w, k & 63);
+                    sts16(q0 + off, hi);
+                    sts16(q0 + 4 * QBOX + off, lo);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(q_ready);
+
+            float mx[WMAX_], lsum[WMAX_];
+#pragma unroll
+            for (int w = 0; w < WMAX_; ++w) { mx[w] = -INFINITY; lsum[w] = 0.0f; }
+            for (int t = 0; t < n_tiles; ++t) {
+                const int row = ROWS * t + e;
+                const bool valid = row < Tm && mask[(size_t)b * Tm + row] != 0;
+                if (!mbar_wait(&s_ready[t], (t == 0 ? ns0++ : ns1++) & 1, abort_flag)) return;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint32_t r[16];
+                tmem_ld16(tlane + 16u * (uint32_t)t, r);
+                tmem_wait_ld16(r);
+                float s[WMAX_], mnew[WMAX_];
+#pragma unroll
+                for (int w = 0; w < WMAX_; ++w) { s[w] = valid ? __uint_as_float(r[w]) : -INFINITY; mnew[w] = s[w]; }
+                reduce16(mnew, true);
+                float scale[WMAX_];
+#pragma unroll
+                for (int w = 0; w < WMAX_; ++w) {
+                    mnew[w] = fmaxf(mx[w], mnew[w]);
+                    scale[w] = (mnew[w] == -INFINITY) ? 1.0f : __expf(mx[w] - mnew[w]);     // mx = -inf, finite new max -> 0
+                    const float pw = (s[w] == -INFINITY) ? 0.0f : __expf(s[w] - mnew[w]);
+                    lsum[w] = lsum[w] * scale[w] + pw;
+                    mx[w] = mnew[w];
+                    s[w] = pw;
+                }
+                if (t > 0) {
+                    // context MMAs of the previous tile have retired: rescale the accumulator (thread e = column e of each half)
+                    if (!mbar_wait(c_done, nc++ & 1, abort_flag)) return;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint32_t c[16];
+                        tmem_ld16(tlane + 32u + 16u * (uint32_t)h, c);
+                        tmem_wait_ld16(c);
+#pragma unroll
+                        for (int w = 0; w < WMAX_; ++w) c[w] = __float_as_uint(__uint_as_float(c[w]) * scale[w]);
+                        tmem_st16(tlane + 32u + 16u * (uint32_t)h, c);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                // probabilities of this tile -> B operand of the context MMAs: P[beam w][row e], fp16 hi / lo
+                for (int w = 0; w < W; ++w) {
+                    uint16_t hi, lo;
+                    split_f16(s[w], hi, lo);
+                    const uint32_t off = (uint32_t)(e >> 6) * QBOX + kmajor_off(w, e & 63);
+                    sts16(p0 + off, hi);
+                    sts16(p0 + 2 * QBOX + off, lo);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(p_ready);
+            }
+            // ---- normalise and write ctx[w, :] into the attention-layer input [h | ctx]
+            reduce16(lsum, false);
+            if (!mbar_wait(c_done, nc++ & 1, abort_flag)) return;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t c[16];
+                tmem_ld16(tlane + 32u + 16u * (uint32_t)h, c);
+                tmem_wait_ld16(c);
+#pragma unroll
+                for (int w = 0; w < WMAX_; ++w)
+                    if (w < W) {
+                        const float inv = (lsum[w] > 0.0f) ? 1.0f / lsum[w] : __int_as_float(0x7fc00000);   // all masked -> NaN like tfa
+                        xa[((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e] = __uint_as_float(c[w]) * inv;
+                    }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+static int make_map3(CUtensorMap *map, const void *base, long long B, int Tm) {
+    gemm::tc::EncodeTiledFn fn = gemm::tc::encode_fn();
+    if (!fn) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)ENC_OUT, (cuuint64_t)Tm, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ENC_OUT * 2, (cuuint64_t)Tm * ENC_OUT * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)ROWS, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(RVB_ERR_CUDA, "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return RVB_OK;
+}
+
+int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
+        int B, int Tm, int W, int *abort_flag, cudaStream_t s) {
+    if (B <= 0) return RVB_OK;
+    if (W < 1 || W > WMAX_ || Tm < 1 || Tm > 2 * ROWS) return fail(RVB_ERR_ARG, "attention_tc: unsupported width %d / memory length %d", W, Tm);
+    CUtensorMap mh, ml;
+    RVB_CHECK(make_map3(&mh, v_hi, B, Tm));
+    RVB_CHECK(make_map3(&ml, v_lo, B, Tm));
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    }
+    const unsigned grid = (unsigned)(B < sms ? B : sms);
+    attention_tc_kernel<<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
+    RVB_LAUNCH_CHECK();
+    return RVB_OK;
+}
+
+}  // namespace atc
+}  // namespace rvb

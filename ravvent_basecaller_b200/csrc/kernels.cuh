@@ -101,6 +101,7 @@ namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >
 struct Params {
     const float *values;        // [B,Tm,256]
     const uint16_t *values16;   // optional fp16 copy of values (reduced-precision mode): the attention kernel streams it instead
+    const uint16_t *v_hi, *v_lo;    // optional fp16 hi / lo planes of values, [B,Tm,256] each: beam widths >= 2 run the tcgen05 attention
     const uint8_t *mask;        // [B,Tm]
     const float *wg_hiT, *wg_loT;   // tf32 hi / lo of [att-input rows ; recurrent kernel], transposed [512,256], [unit][gate] columns
     const float *wm_hiT, *wm_loT;   // W_mem^T as a [K=128, N=256] weight, transposed [256,128]
@@ -122,5 +123,10 @@ struct Params {
 size_t workspace_floats(long long rows, int depth = 1);
 int run(const Params &p, cudaStream_t stream);
 }  // namespace decw
+
+namespace atc {     // K4 attention on tcgen05 for beam widths >= 2, attention_tc.cu
+int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
+        int B, int Tm, int W, int *abort_flag, cudaStream_t s);
+}  // namespace atc
 
 }  // namespace rvb

@@ -86,3 +86,42 @@ def test_float32_differences_are_near_ties(encoded):
         else:
             assert np.array_equal(pa[r, :T], pb[r, :T])
     assert differing <= n // 50, differing
+
+
+@pytest.mark.parametrize("rnn_type", ["gru", "bigru", "lstm"])
+def test_rnn_type_variants_agree(rnn_type):
+    """GRU cells (Keras reset_after=True vs torch.nn.GRUCell) and unidirectional encoders (basecaller.py:25-46, 86-89)."""
+    w = mr.init_weights(9, rnn_type=rnn_type, random_bias=True)
+    x = mr.synth_chunks(np.random.default_rng(6), 48)
+    enc, mask = mr.encode_input(w, x, "joint")
+    assert enc.shape == (48, 230, 256 if "bi" in rnn_type else 128)
+    a = mr.beam_search(w, enc, mask, 5, 20, dtype=np.float64, return_all=True)
+    t = mt.beam_search(w, enc, mask, 5, 20, dtype=torch.float64, return_all=True)
+    assert np.array_equal(a[0], t[0]) and np.array_equal(a[2], t[2]) and np.array_equal(a[3], t[3])
+    gi, gl = mr.greedy_search(w, enc, mask, 20, dtype=np.float64)
+    ti, tl = mt.greedy_search(w, enc, mask, 20, dtype=torch.float64)
+    assert np.array_equal(gi, ti)
+    np.testing.assert_allclose(gl, tl, rtol=1e-9, atol=1e-9)
+
+
+def test_gru_encoder_matches_torch_gru():
+    """Encoder GRU layers against torch.nn.GRU (bidirectional, state hand-off as Encoder.call does it)."""
+    u = 32
+    w = mr.init_weights(5, enc_units=u, dec_units=u, rnn_type="bigru", random_bias=True)
+    x = np.random.default_rng(0).normal(size=(6, 37, 1)).astype(np.float32)
+    out, states = mr.encoder(x, w, "encoder_raw", 2, u)
+    y = torch.from_numpy(x)
+    h0 = torch.zeros(2, 6, u)
+    perm = np.concatenate([np.arange(u, 2 * u), np.arange(0, u), np.arange(2 * u, 3 * u)])
+    for l in range(2):
+        gru = torch.nn.GRU(y.shape[-1], u, batch_first=True, bidirectional=True)
+        with torch.no_grad():
+            for d, suf in (("forward", ""), ("backward", "_reverse")):
+                getattr(gru, "weight_ih_l0" + suf).copy_(torch.from_numpy(w[f"encoder_raw/layer{l}/{d}/kernel"].T[perm].copy()))
+                getattr(gru, "weight_hh_l0" + suf).copy_(torch.from_numpy(w[f"encoder_raw/layer{l}/{d}/recurrent_kernel"].T[perm].copy()))
+                getattr(gru, "bias_ih_l0" + suf).copy_(torch.from_numpy(w[f"encoder_raw/layer{l}/{d}/bias"][0][perm].copy()))
+                getattr(gru, "bias_hh_l0" + suf).copy_(torch.from_numpy(w[f"encoder_raw/layer{l}/{d}/bias"][1][perm].copy()))
+            y, h0 = gru(y, h0)
+    np.testing.assert_allclose(out, y.numpy(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(states[0], h0[0].numpy(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(states[2], h0[1].numpy(), rtol=1e-4, atol=2e-6)
