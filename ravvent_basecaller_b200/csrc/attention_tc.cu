@@ -62,6 +62,17 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, u
     d |= (uint64_t)2 << 61;
     return d;
 }
+// tcgen05.mma with the descriptors given as (low word, high word): the issuer keeps base words and adds immediates
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -94,6 +105,7 @@ __device__ __forceinline__ uint32_t kmajor_off(int n, int k) {
     return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
+template <int WT>       // beam bucket: loops over beams are unrolled to WT (5 or 9)
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const uint8_t *__restrict__ mask, const float *__restrict__ Q, float *__restrict__ xa,
@@ -156,32 +168,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             constexpr uint32_t idesc_c = make_idesc_f16(ROWS, NB) | (1u << 15);      // A MN-major (V^T), B K-major
             const uint32_t q0 = smem_u32(qbuf), p0 = smem_u32(pbuf), r0 = smem_u32(ring);
             uint32_t n = 0, nq = 0, np = 0;                           // units consumed, q_ready / p_ready phases seen
+            // descriptor words: low = (address >> 4) | LBO field, high = SBO | version | swizzle; one thread issues ~100 tiny MMAs
+            // per tile, so every instruction of descriptor arithmetic counts
+            const uint64_t dk = make_desc(0), dm = make_desc_mn(0, BOX_BYTES, 1024);
+            const uint32_t k_lo = (uint32_t)dk, k_hi = (uint32_t)(dk >> 32), m_lo = (uint32_t)dm, m_hi = (uint32_t)(dm >> 32);
+            const uint32_t qw = k_lo + (q0 >> 4), pw = k_lo + (p0 >> 4);
             // scores of unit (t, h): 128 columns of K = 2 boxes x 4 k-steps, 3 split passes
             auto scores_unit = [&](uint32_t ubase, int t, int h) {
+                const uint32_t aw = k_lo + (ubase >> 4);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const int pa = (pass == 0) ? 1 : 0, pb = (pass == 1) ? 1 : 0;       // V_lo.Q_hi, V_hi.Q_lo, V_hi.Q_hi
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = make_desc(ubase + (pa * 2 + jj) * BOX_BYTES + ks * 32);
-                            const uint64_t bd = make_desc(q0 + pb * (4 * QBOX) + (2 * h + jj) * QBOX + ks * 32);
-                            umma_f16(tmem_base + 16u * (uint32_t)t, ad, bd, idesc_s, (h | pass | jj | ks) ? 1u : 0u);
-                        }
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16_w(tmem_base + 16u * (uint32_t)t, aw + (uint32_t)(((pa * 2 + jj) * BOX_BYTES + ks * 32) >> 4), k_hi,
+                                       qw + (uint32_t)((pb * (4 * QBOX) + (2 * h + jj) * QBOX + ks * 32) >> 4), k_hi, idesc_s,
+                                       (h | pass | jj | ks) ? 1u : 0u);
                 }
             };
             // context of unit (t, h): columns 128h..128h+127 (M), this tile's 128 rows (K = 8 k-steps of 16), 3 split passes
             auto ctx_unit = [&](uint32_t ubase, int t, int h) {
+                const uint32_t aw = m_lo + (ubase >> 4);
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const int pa = (pass == 0) ? 1 : 0, pb = (pass == 1) ? 1 : 0;
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint64_t ad = make_desc_mn(ubase + pa * 2 * BOX_BYTES + ks * 2048, BOX_BYTES, 1024);
-                        const uint64_t bd = make_desc(p0 + pb * (2 * QBOX) + (ks >> 2) * QBOX + (ks & 3) * 32);
-                        umma_f16(tmem_base + 32u + 16u * (uint32_t)h, ad, bd, idesc_c, (t | pass | ks) ? 1u : 0u);
-                    }
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16_w(tmem_base + 32u + 16u * (uint32_t)h, aw + (uint32_t)((pa * 2 * BOX_BYTES + ks * 2048) >> 4), m_hi,
+                                   pw + (uint32_t)((pb * (2 * QBOX) + (ks >> 2) * QBOX + (ks & 3) * 32) >> 4), k_hi, idesc_c,
+                                   (t | pass | ks) ? 1u : 0u);
                 }
             };
             auto wait_unit = [&](uint32_t k) -> bool { return mbar_wait(&full[k % RING], (k / RING) & 1, abort_flag); };
@@ -229,9 +246,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         const uint32_t tlane = tmem_base + ((uint32_t)(32 * qd) << 16);
         const uint32_t q0 = smem_u32(qbuf), p0 = smem_u32(pbuf);
         uint32_t ns0 = 0, ns1 = 0, nc = 0, nred = 0;
-        auto reduce16 = [&](float (&v)[WMAX_], bool is_max) {        // all-reduce over the 128 softmax threads, per beam
+        auto reduce16 = [&](float (&v)[WT], bool is_max) {        // all-reduce over the 128 softmax threads, per beam
 #pragma unroll
-            for (int w = 0; w < WMAX_; ++w)
+            for (int w = 0; w < WT; ++w)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     const float other = __shfl_xor_sync(0xffffffffu, v[w], o);
@@ -240,50 +257,64 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             float *buf = red + (nred++ & 1) * 64;
             if (lane == 0) {
 #pragma unroll
-                for (int w = 0; w < WMAX_; ++w) buf[(warp - 2) * 16 + w] = v[w];
+                for (int w = 0; w < WT; ++w) buf[(warp - 2) * 16 + w] = v[w];
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-            for (int w = 0; w < WMAX_; ++w) {
+            for (int w = 0; w < WT; ++w) {
                 const float a = buf[w], b2 = buf[16 + w], c2 = buf[32 + w], d2 = buf[48 + w];
                 v[w] = is_max ? fmaxf(fmaxf(a, b2), fmaxf(c2, d2)) : (a + b2) + (c2 + d2);
             }
         };
-        for (int b = blockIdx.x; b < B; b += gridDim.x) {
-            if (skip[b]) continue;
-            // ---- queries of this snippet -> fp16 hi / lo B tiles (the previous snippet's score MMAs have retired: s_ready seen)
-            for (int w = 0; w < W; ++w) {
+        // queries of a snippet -> fp16 hi / lo B tiles
+        auto write_q = [&](int b) {
+            float qv[WT][2];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int k = e + 128 * half;
-                    uint16_t hi, lo;
-                    split_f16(__ldg(Q + ((size_t)b * W + w) * ENC_OUT + k), hi, lo);
-                    const uint32_t off = (uint32_t)(k >> 6) * QBOX + kmajor_off(w, k & 63);
-                    sts16(q0 + off, hi);
-                    sts16(q0 + 4 * QBOX + off, lo);
+            for (int w = 0; w < WT; ++w)            // all loads first: one round trip to L2 instead of 2 W dependent ones
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+                    qv[w][half] = (w < W) ? __ldg(Q + ((size_t)b * W + w) * ENC_OUT + e + 128 * half) : 0.0f;
+#pragma unroll
+            for (int w = 0; w < WT; ++w)
+                if (w < W) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        const int k = e + 128 * half;
+                        uint16_t hi, lo;
+                        split_f16(qv[w][half], hi, lo);
+                        const uint32_t off = (uint32_t)(k >> 6) * QBOX + kmajor_off(w, k & 63);
+                        sts16(q0 + off, hi);
+                        sts16(q0 + 4 * QBOX + off, lo);
+                    }
                 }
-            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(q_ready);
-
-            float mx[WMAX_], lsum[WMAX_];
+        };
+        auto next_live = [&](int b) { b += gridDim.x; while (b < B && skip[b]) b += gridDim.x; return b; };
+        int b = (int)blockIdx.x;
+        while (b < B && skip[b]) b += gridDim.x;
+        if (b < B) write_q(b);
+        for (; b < B; b = next_live(b)) {
+            float mx[WT], lsum[WT];
 #pragma unroll
-            for (int w = 0; w < WMAX_; ++w) { mx[w] = -INFINITY; lsum[w] = 0.0f; }
+            for (int w = 0; w < WT; ++w) { mx[w] = -INFINITY; lsum[w] = 0.0f; }
+            uint8_t mk[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) mk[t] = (ROWS * t + e < Tm) ? __ldg(mask + (size_t)b * Tm + ROWS * t + e) : (uint8_t)0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int row = ROWS * t + e;
-                const bool valid = row < Tm && mask[(size_t)b * Tm + row] != 0;
+                const bool valid = mk[t] != 0;
                 if (!mbar_wait(&s_ready[t], (t == 0 ? ns0++ : ns1++) & 1, abort_flag)) return;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t r[16];
                 tmem_ld16(tlane + 16u * (uint32_t)t, r);
                 tmem_wait_ld16(r);
-                float s[WMAX_], mnew[WMAX_];
+                float s[WT], mnew[WT];
 #pragma unroll
-                for (int w = 0; w < WMAX_; ++w) { s[w] = valid ? __uint_as_float(r[w]) : -INFINITY; mnew[w] = s[w]; }
+                for (int w = 0; w < WT; ++w) { s[w] = valid ? __uint_as_float(r[w]) : -INFINITY; mnew[w] = s[w]; }
                 reduce16(mnew, true);
-                float scale[WMAX_];
+                float scale[WT];
 #pragma unroll
-                for (int w = 0; w < WMAX_; ++w) {
+                for (int w = 0; w < WT; ++w) {
                     mnew[w] = fmaxf(mx[w], mnew[w]);
                     scale[w] = (mnew[w] == -INFINITY) ? 1.0f : __expf(mx[w] - mnew[w]);     // mx = -inf, finite new max -> 0
                     const float pw = (s[w] == -INFINITY) ? 0.0f : __expf(s[w] - mnew[w]);
@@ -301,22 +332,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         tmem_ld16(tlane + 32u + 16u * (uint32_t)h, c);
                         tmem_wait_ld16(c);
 #pragma unroll
-                        for (int w = 0; w < WMAX_; ++w) c[w] = __float_as_uint(__uint_as_float(c[w]) * scale[w]);
+                        for (int w = 0; w < WT; ++w) c[w] = __float_as_uint(__uint_as_float(c[w]) * scale[w]);
                         tmem_st16(tlane + 32u + 16u * (uint32_t)h, c);
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 // probabilities of this tile -> B operand of the context MMAs: P[beam w][row e], fp16 hi / lo
-                for (int w = 0; w < W; ++w) {
-                    uint16_t hi, lo;
-                    split_f16(s[w], hi, lo);
-                    const uint32_t off = (uint32_t)(e >> 6) * QBOX + kmajor_off(w, e & 63);
-                    sts16(p0 + off, hi);
-                    sts16(p0 + 2 * QBOX + off, lo);
-                }
+#pragma unroll
+                for (int w = 0; w < WT; ++w)
+                    if (w < W) {
+                        uint16_t hi, lo;
+                        split_f16(s[w], hi, lo);
+                        const uint32_t off = (uint32_t)(e >> 6) * QBOX + kmajor_off(w, e & 63);
+                        sts16(p0 + off, hi);
+                        sts16(p0 + 2 * QBOX + off, lo);
+                    }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(p_ready);
+            }
+            // The score MMAs of this snippet have retired (s_ready of its last tile was seen): the next snippet's queries can
+            // go in now, so that its score MMAs are issued while this snippet's last context MMAs and output are in flight.
+            {
+                const int bn = next_live(b);
+                if (bn < B) write_q(bn);
             }
             // ---- normalise and write ctx[w, :] into the attention-layer input [h | ctx]
             reduce16(lsum, false);
@@ -328,7 +367,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                 tmem_ld16(tlane + 32u + 16u * (uint32_t)h, c);
                 tmem_wait_ld16(c);
 #pragma unroll
-                for (int w = 0; w < WMAX_; ++w)
+                for (int w = 0; w < WT; ++w)
                     if (w < W) {
                         const float inv = (lsum[w] > 0.0f) ? 1.0f / lsum[w] : __int_as_float(0x7fc00000);   // all masked -> NaN like tfa
                         xa[((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e] = __uint_as_float(c[w]) * inv;
@@ -370,10 +409,12 @@ int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const f
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+        RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     }
     const unsigned grid = (unsigned)(B < sms ? B : sms);
-    attention_tc_kernel<<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
+    if (W <= 5) attention_tc_kernel<5><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
+    else attention_tc_kernel<9><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
 }
