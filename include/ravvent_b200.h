@@ -44,6 +44,8 @@ extern "C" {
 #define RVB_INPUT_JOINT    2
 
 #define RVB_PREC_FP32      0   /* parity mode: split-precision (3-pass) tensor-core products, fp32-accurate     */
+#define RVB_CELL_LSTM      0   /* rvb_model_set_rnn cell_kind */
+#define RVB_CELL_GRU       1
 #define RVB_PREC_BF16      1   /* reduced mode: single 16-bit pass, fp32 accumulate / cell state, fp16 attention memory */
 
 typedef struct rvb_model rvb_model_t;
@@ -108,6 +110,12 @@ int rvb_build_snippets(const void *d_signal, int sample_bytes, int64_t n_samples
 int rvb_model_create(rvb_model_t **out, int device, int enc_units, int dec_units,
                      int encoder_depth, int decoder_depth, int vocab_size,
                      int input_kind, int precision, int wave_snippets);
+/* rnn_type of the reference constructor (basecaller.py:25-46, 86-89, 195): 'bi*' -> bidirectional = 1; '*lstm' / '*gru' ->
+ * cell_kind.  The default after rvb_model_create is ('bilstm': 1, RVB_CELL_LSTM).  Call before rvb_model_finalize.
+ * GRU weights: kernel [in,3u], recurrent_kernel [u,3u], bias [2,3u] (Keras reset_after = True); unidirectional
+ * encoders have no ".../backward/..." weights and layers > 0 / the decoder's memory and attention layers take
+ * enc_units instead of 2*enc_units inputs. */
+int rvb_model_set_rnn(rvb_model_t *m, int bidirectional, int cell_kind);
 int rvb_model_destroy(rvb_model_t *m);
 /* name as in the .npz interchange (oracle/model_ref.py init_weights), e.g.
  * "encoder_raw/layer0/forward/kernel"; row-major float32 host data. */

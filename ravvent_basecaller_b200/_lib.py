@@ -12,6 +12,7 @@ _SO = Path(__file__).resolve().parent / "libravvent_b200.so"
 RVB_OK, RVB_ERR_ARG, RVB_ERR_CUDA, RVB_ERR_STATE, RVB_ERR_OVERFLOW, RVB_ERR_INTERNAL = range(6)
 INPUT_KIND = {"raw": 0, "event": 1, "joint": 2}
 PRECISION = {"fp32": 0, "bf16": 1}
+CELL_KIND = {"lstm": 0, "gru": 1}
 
 
 class RavventError(RuntimeError):
@@ -40,6 +41,7 @@ _PROTOS = {
     "rvb_build_snippets": (_i, [_p, _i, _i64, _p, _p, _p, _p, C.c_int32, _i64, _i64, C.c_int32, _p, _p, C.c_int32, _p, _p, _p]),
     "rvb_model_create": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "rvb_model_destroy": (_i, [_p]),
+    "rvb_model_set_rnn": (_i, [_p, _i, _i]),
     "rvb_model_set_weight": (_i, [_p, C.c_char_p, _p, _p, _i]),
     "rvb_model_finalize": (_i, [_p]),
     "rvb_model_check": (_i, [_p]),

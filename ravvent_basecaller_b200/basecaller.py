@@ -25,8 +25,8 @@ class Basecaller:
                  device: int | None = None, precision: str = 'fp32', wave_snippets: int = 0):
         if input_data_type not in ('raw', 'event', 'joint'):
             raise ValueError("input_data_type must be 'raw', 'event' or 'joint'")
-        if rnn_type != 'bilstm':
-            raise NotImplementedError("only rnn_type='bilstm' is built (the configuration every reference script uses)")
+        if rnn_type not in ('bilstm', 'lstm', 'bigru', 'gru'):
+            raise NotImplementedError("rnn_type must be one of 'gru', 'lstm', 'bigru', 'bilstm' (basecaller.py:167)")
         if float(input_padding_value) != 0.0:
             raise NotImplementedError("input_padding_value must be 0.0 (data_loader.INPUT_PADDING)")
         self.batch_sz = batch_sz
@@ -60,6 +60,9 @@ class Basecaller:
         _lib.check(_lib.lib.rvb_model_create(C.byref(self._h), dev, self.enc_units, self.dec_units, self.encoder_depth,
                                              self.decoder_depth, self.vocab_size, _lib.INPUT_KIND[input_data_type],
                                              _lib.PRECISION[precision], int(wave_snippets)))
+        if rnn_type != 'bilstm':      # 'bi' -> Bidirectional encoders; the cell kind also applies to the decoder (basecaller.py:195)
+            _lib.check(_lib.lib.rvb_model_set_rnn(self._h, 1 if 'bi' in rnn_type else 0,
+                                                  _lib.CELL_KIND['lstm' if 'lstm' in rnn_type else 'gru']))
         self._weights_loaded = False
 
     def __del__(self):
@@ -79,7 +82,7 @@ class Basecaller:
         or seed= for Keras-default random initialisation."""
         if source is None:
             w = _weights.random_weights(22 if seed is None else seed, self.enc_units, self.dec_units,
-                                        self.encoder_depth, self.decoder_depth, self.vocab_size)
+                                        self.encoder_depth, self.decoder_depth, self.vocab_size, self.rnn_type)
         elif isinstance(source, dict):
             w = source
         else:
@@ -156,6 +159,8 @@ class Basecaller:
                                            enc.data_ptr(), mask.data_ptr(), self._stream()))
         _lib.check(_lib.lib.rvb_model_check(self._h))
         mask = mask.bool()
+        if 'bi' not in self.rnn_type:        # unidirectional encoders: the memory is enc_units wide (the internal backward half is all zeros)
+            enc = enc[:, :, :self.enc_units].contiguous()
         if host:
             return enc.cpu().numpy(), mask.cpu().numpy()
         return enc, mask

@@ -83,6 +83,8 @@ struct rvb_model {
     uint16_t *enc_out16 = nullptr;             // fp16 copy of enc_out (reduced-precision mode only)
     uint16_t *enc_hi = nullptr, *enc_lo = nullptr;   // fp16 hi / lo planes of the memory (tcgen05 attention, beam widths >= 2)
     bool att_tc = false;
+    bool bidir = true;                         // rnn_type 'bi*': Bidirectional encoders; otherwise the backward direction has zero weights (outputs exactly 0)
+    int cell = RVB_CELL_LSTM;                  // LSTM or GRU cells (encoders and decoder)
     uint8_t *mask = nullptr;
     int32_t *step_ids = nullptr, *parent_ids = nullptr;
     // host-buffer variant: double-buffered I/O sets, pinned staging, copy streams (HostPipe, below)
@@ -160,6 +162,17 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     return RVB_OK;
 }
 
+extern "C" int rvb_model_set_rnn(rvb_model_t *m, int bidirectional, int cell_kind) {
+    if (!m) return fail(RVB_ERR_ARG, "null model");
+    if (cell_kind != RVB_CELL_LSTM && cell_kind != RVB_CELL_GRU) return fail(RVB_ERR_ARG, "cell_kind must be RVB_CELL_LSTM or RVB_CELL_GRU");
+    if ((cell_kind == RVB_CELL_GRU || !bidirectional) && !(m->rec_tc && m->dec_wave))
+        return fail(RVB_ERR_STATE, "GRU / unidirectional models need the tensor-core recurrence and the wave decoder (unset RVB_REC / RVB_DECODER / RVB_GEMM)");
+    m->bidir = bidirectional != 0;
+    m->cell = cell_kind;
+    m->finalized = false;
+    return RVB_OK;
+}
+
 extern "C" int rvb_model_destroy(rvb_model_t *m) {
     if (!m) return RVB_OK;
     cudaSetDevice(m->device);
@@ -189,6 +202,44 @@ static int get_w(rvb_model *m, const std::string &name, int64_t d0, int64_t d1, 
     bool ok = d1 < 0 ? (t.shape.size() == 1 && t.shape[0] == d0) : (t.shape.size() == 2 && t.shape[0] == d0 && t.shape[1] == d1);
     if (!ok) return fail(RVB_ERR_ARG, "weight '%s' has the wrong shape", name.c_str());
     *out = &t;
+    return RVB_OK;
+}
+
+// One recurrent cell in the internal "four gate blocks of `UNITS` columns" form every packer below consumes:
+//   LSTM: Keras kernel [F,4u] / recurrent_kernel [u,4u] / bias [4u] as they are (blocks i, f, g, o);
+//   GRU (Keras reset_after = True: kernel [F,3u], recurrent_kernel [u,3u], bias [2,3u], blocks z, r, h):
+//        W4 = [W_z | W_r | W_h | 0],  U4 = [U_z | U_r | 0 | U_h],  b4 = [b_iz + b_rz | b_ir + b_rr | b_ih | b_rh]
+//     so that column block 2 is the INPUT part of the candidate and block 3 its RECURRENT part (bias included): the cell
+//     epilogues compute z = s(s0), r = s(s1), h~ = tanh(s2 + r s3) on the same summed pre-activations an LSTM uses;
+//   a missing direction / zero-padded input rows (unidirectional encoders: F_in < F): zeros -- a cell with all-zero
+//     weights and a zero state outputs exactly 0, which is what the absent backward half of the memory must be.
+struct Cell4 { std::vector<float> W, U, b; };      // [F][512], [128][512], [512]
+static int get_cell4(rvb_model *m, const std::string &base, int F, int F_in, bool required, Cell4 *out) {
+    out->W.assign((size_t)F * GATES, 0.0f); out->U.assign((size_t)UNITS * GATES, 0.0f); out->b.assign(GATES, 0.0f);
+    if (!required && m->hw.find(base + "kernel") == m->hw.end()) return RVB_OK;
+    const int G = m->cell == RVB_CELL_GRU ? 3 * UNITS : GATES;
+    const HostTensor *W, *U, *Bv;
+    RVB_CHECK(get_w(m, base + "kernel", F_in, G, &W));
+    RVB_CHECK(get_w(m, base + "recurrent_kernel", UNITS, G, &U));
+    if (m->cell == RVB_CELL_GRU) RVB_CHECK(get_w(m, base + "bias", 2, G, &Bv)); else RVB_CHECK(get_w(m, base + "bias", G, -1, &Bv));
+    if (m->cell != RVB_CELL_GRU) {
+        for (int k = 0; k < F_in; ++k) std::copy(W->data.begin() + (size_t)k * GATES, W->data.begin() + (size_t)(k + 1) * GATES, out->W.begin() + (size_t)k * GATES);
+        out->U = U->data; out->b = Bv->data;
+        return RVB_OK;
+    }
+    for (int u = 0; u < UNITS; ++u) {
+        for (int k = 0; k < F_in; ++k)
+            for (int g = 0; g < 3; ++g) out->W[(size_t)k * GATES + g * UNITS + u] = W->data[(size_t)k * G + g * UNITS + u];
+        for (int k = 0; k < UNITS; ++k) {
+            out->U[(size_t)k * GATES + 0 * UNITS + u] = U->data[(size_t)k * G + 0 * UNITS + u];
+            out->U[(size_t)k * GATES + 1 * UNITS + u] = U->data[(size_t)k * G + 1 * UNITS + u];
+            out->U[(size_t)k * GATES + 3 * UNITS + u] = U->data[(size_t)k * G + 2 * UNITS + u];
+        }
+        out->b[0 * UNITS + u] = Bv->data[0 * UNITS + u] + Bv->data[G + 0 * UNITS + u];
+        out->b[1 * UNITS + u] = Bv->data[1 * UNITS + u] + Bv->data[G + 1 * UNITS + u];
+        out->b[2 * UNITS + u] = Bv->data[2 * UNITS + u];
+        out->b[3 * UNITS + u] = Bv->data[G + 2 * UNITS + u];
+    }
     return RVB_OK;
 }
 
@@ -232,10 +283,13 @@ static int finalize_impl(rvb_model *m) {
             std::vector<float> w0(m->rec_tc && l == 0 ? (size_t)2 * rectc::W0_FLOATS_PER_DIR : 0, 0.0f);
             for (int d = 0; d < 2; ++d) {
                 std::string base = std::string(enc_name[e]) + "/layer" + std::to_string(l) + "/" + dir_name[d] + "/";
-                const HostTensor *W, *U, *Bv;
-                RVB_CHECK(get_w(m, base + "kernel", F, GATES, &W));
-                RVB_CHECK(get_w(m, base + "recurrent_kernel", UNITS, GATES, &U));
-                RVB_CHECK(get_w(m, base + "bias", GATES, -1, &Bv));
+                // unidirectional encoders: no backward weights, and layers > 0 see enc_units inputs instead of 2 enc_units
+                Cell4 c4;
+                const bool present = d == 0 || m->bidir;
+                if (present) RVB_CHECK(get_cell4(m, base, F, (l > 0 && !m->bidir) ? UNITS : F, true, &c4));
+                else RVB_CHECK(get_cell4(m, base, F, F, false, &c4));
+                struct { std::vector<float> &data; } Wr{c4.W}, Ur{c4.U}, Br{c4.b};
+                auto *W = &Wr, *U = &Ur, *Bv = &Br;
                 for (int r = 0; r < 2; ++r)
                     for (int k = 0; k < KX; ++k)
                         for (int g = 0; g < 4; ++g)
@@ -291,12 +345,20 @@ static int finalize_impl(rvb_model *m) {
         }
     }
     {
-        const HostTensor *Wd, *Ud, *Bd, *Wm, *Wa, *Wf, *Bf;
-        RVB_CHECK(get_w(m, "decoder/cell0/kernel", VOCAB + UNITS, GATES, &Wd));
-        RVB_CHECK(get_w(m, "decoder/cell0/recurrent_kernel", UNITS, GATES, &Ud));
-        RVB_CHECK(get_w(m, "decoder/cell0/bias", GATES, -1, &Bd));
-        RVB_CHECK(get_w(m, "decoder/memory_layer/kernel", ENC_OUT, UNITS, &Wm));
-        RVB_CHECK(get_w(m, "decoder/attention_layer/kernel", UNITS + ENC_OUT, UNITS, &Wa));
+        const HostTensor *Wm_in, *Wa_in, *Wf, *Bf;
+        Cell4 d0;
+        RVB_CHECK(get_cell4(m, "decoder/cell0/", VOCAB + UNITS, VOCAB + UNITS, true, &d0));
+        struct { std::vector<float> &data; } Wdr{d0.W}, Udr{d0.U}, Bdr{d0.b};
+        auto *Wd = &Wdr, *Ud = &Udr, *Bd = &Bdr;
+        // unidirectional encoders: the memory is enc_units wide; its absent backward half is zero, so are the rows that read it
+        const int mem_w = m->bidir ? ENC_OUT : UNITS;
+        RVB_CHECK(get_w(m, "decoder/memory_layer/kernel", mem_w, UNITS, &Wm_in));
+        RVB_CHECK(get_w(m, "decoder/attention_layer/kernel", UNITS + mem_w, UNITS, &Wa_in));
+        HostTensor Wm_pad, Wa_pad;
+        Wm_pad.data.assign((size_t)ENC_OUT * UNITS, 0.0f); Wa_pad.data.assign((size_t)(UNITS + ENC_OUT) * UNITS, 0.0f);
+        std::copy(Wm_in->data.begin(), Wm_in->data.end(), Wm_pad.data.begin());
+        std::copy(Wa_in->data.begin(), Wa_in->data.end(), Wa_pad.data.begin());
+        const HostTensor *Wm = &Wm_pad, *Wa = &Wa_pad;
         RVB_CHECK(get_w(m, "decoder/fc/kernel", UNITS, VOCAB, &Wf));
         RVB_CHECK(get_w(m, "decoder/fc/bias", VOCAB, -1, &Bf));
         std::vector<float> wg((size_t)2 * UNITS * UNITS * 4), wtok((size_t)VOCAB * UNITS * 4);
@@ -311,10 +373,10 @@ static int finalize_impl(rvb_model *m) {
                     wtok[((size_t)v * UNITS + u) * 4 + g] = Wd->data[(size_t)v * GATES + g * UNITS + u] + Bd->data[g * UNITS + u];
         RVB_CHECK(upload(m, &m->d_wg, wg));
         if (m->dec_depth == 2) {
-            const HostTensor *W1, *U1, *B1;
-            RVB_CHECK(get_w(m, "decoder/cell1/kernel", UNITS, GATES, &W1));
-            RVB_CHECK(get_w(m, "decoder/cell1/recurrent_kernel", UNITS, GATES, &U1));
-            RVB_CHECK(get_w(m, "decoder/cell1/bias", GATES, -1, &B1));
+            Cell4 d1;
+            RVB_CHECK(get_cell4(m, "decoder/cell1/", UNITS, UNITS, true, &d1));
+            struct { std::vector<float> &data; } W1r{d1.W}, U1r{d1.U}, B1r{d1.b};
+            auto *W1 = &W1r, *U1 = &U1r, *B1 = &B1r;
             std::vector<float> wg1((size_t)2 * UNITS * UNITS * 4), b1((size_t)UNITS * 4);
             for (int k = 0; k < 2 * UNITS; ++k)
                 for (int u = 0; u < UNITS; ++u)
@@ -359,10 +421,10 @@ static int finalize_impl(rvb_model *m) {
             RVB_CHECK(upload(m, &m->dw_wtok, wtk));
             if (m->dec_depth == 2) {
                 // second stacked cell: [kernel (input = h of cell 0) ; recurrent kernel] as one [256,512] weight, [unit][gate] columns
-                const HostTensor *W1, *U1, *B1;
-                RVB_CHECK(get_w(m, "decoder/cell1/kernel", UNITS, GATES, &W1));
-                RVB_CHECK(get_w(m, "decoder/cell1/recurrent_kernel", UNITS, GATES, &U1));
-                RVB_CHECK(get_w(m, "decoder/cell1/bias", GATES, -1, &B1));
+                Cell4 d1;
+                RVB_CHECK(get_cell4(m, "decoder/cell1/", UNITS, UNITS, true, &d1));
+                struct { std::vector<float> &data; } W1r{d1.W}, U1r{d1.U}, B1r{d1.b};
+                auto *W1 = &W1r, *U1 = &U1r, *B1 = &B1r;
                 std::vector<float> w1cat((size_t)2 * UNITS * GATES), b1v(GATES);
                 for (int k = 0; k < 2 * UNITS; ++k)
                     for (int n = 0; n < GATES; ++n)
@@ -462,7 +524,7 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
             p.y16_bs = (long long)Tm * ENC_OUT; p.y16_ts = ENC_OUT;
         }
         p.yv16 = (last && m->enc_out16 != nullptr && out == m->enc_out) ? m->enc_out16 + (size_t)t_off * ENC_OUT : nullptr;
-        p.B = nb; p.T = T; p.abort_flag = m->d_abort; p.precision = m->precision;
+        p.B = nb; p.T = T; p.abort_flag = m->d_abort; p.precision = m->precision; p.gru = m->cell == RVB_CELL_GRU;
         if (l > 0) {
             const uint16_t *a_hi = reinterpret_cast<const uint16_t *>(yb[(l - 1) & 1]);
             // rows b >= nb of a timestep are padding: never written by K3, projected as they are, never read back
@@ -556,7 +618,9 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s, tc_att));
         // Wave-level decoder for every beam width (reduced-precision mode: its attention kernel streams the fp16 copy of the
         // memory).  Greedy search keeps the persistent kernel.
-        if (beam && m->dec_wave) {
+        static const bool greedy_persistent = getenv("RVB_GREEDY") && strcmp(getenv("RVB_GREEDY"), "persistent") == 0;
+        if (m->dec_wave && (beam || !greedy_persistent || m->cell == RVB_CELL_GRU)) {
+            if (!beam) W = 1;
             const size_t rows = (size_t)m->wave * W;
             if (rows > m->dw_ws_rows) {
                 dfree(m, m->dw_ws);
@@ -573,14 +637,17 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];
             q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
             q.wg1_16_hi = m->dw_wg1_16[0]; q.wg1_16_lo = m->dw_wg1_16[1]; q.b1 = m->dw_b1; q.depth = m->dec_depth;
+            q.gru = m->cell == RVB_CELL_GRU; q.greedy = beam ? 0 : 1;
+            q.logits = beam ? nullptr : d_logits + (size_t)b0 * S * VOCAB;
             q.B = nb; q.Tm = Tm; q.W = W; q.S = S;
-            q.ids = d_ids + (size_t)b0 * S * W; q.scores = d_scores + (size_t)b0 * S * W;
+            q.ids = d_ids + (size_t)b0 * S * W; q.scores = beam ? d_scores + (size_t)b0 * S * W : nullptr;
             q.step_ids = d_step_ids ? d_step_ids + (size_t)b0 * S * W : m->step_ids;
             q.parent_ids = d_parent_ids ? d_parent_ids + (size_t)b0 * S * W : m->parent_ids;
             q.steps = d_steps; q.ws = m->dw_ws; q.abort_flag = m->d_abort;
             RVB_CHECK(decw::run(q, s));
             continue;
         }
+        if (m->cell == RVB_CELL_GRU) return fail(RVB_ERR_STATE, "the persistent decoder kernel implements LSTM cells only");
         dec::Params p{};
         p.wmemT = m->d_wmemT; p.values = m->enc_out; p.values16 = m->enc_out16; p.mask = m->mask;
         p.wg = m->d_wg; p.wtok = m->d_wtok; p.wg1 = m->d_wg1; p.b1 = m->d_b1; p.depth = m->dec_depth; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
                                                         int B, int W, int S, int t, const float *__restrict__ xa, float *__restrict__ X,
                                                         uint16_t *__restrict__ x_hi, uint16_t *__restrict__ x_lo,
                                                         const float *__restrict__ h0, uint16_t *__restrict__ x1_hi, uint16_t *__restrict__ x1_lo,
-                                                        int32_t *__restrict__ skip) {
+                                                        int32_t *__restrict__ skip, float *__restrict__ greedy_logits, int32_t *__restrict__ greedy_ids) {
     __shared__ float a_s[4][WMAX * UNITS];
     __shared__ float lg_s[4][WMAX * 8];
     __shared__ float wfc_s[UNITS * VOCAB];
@@ -213,6 +213,22 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     __syncwarp();
     const int n_cand = W * VOCAB;
     const size_t r0 = (size_t)b * W;
+    if (greedy_logits != nullptr) {
+        // BasicDecoder + GreedyEmbeddingSampler, W == 1: sample = argmax (ties -> lowest index), no masking of
+        // finished rows (impute_finished = False: they keep decoding); T = first step at which every row has emitted the end token
+        float v = (lane < VOCAB) ? lg_s[wid][lane] : -INFINITY;
+        int i = (lane < VOCAB) ? lane : 0x7fffffff;
+        if (lane < VOCAB) greedy_logits[((size_t)b * S + t) * VOCAB + lane] = v;
+        warp_argmax(v, i);
+        if (lane == 0) {
+            greedy_ids[(size_t)b * S + t] = i;
+            tok[r0] = i; parent[r0] = 0;
+            if (i == TOKEN_END && first_done[b] == S) first_done[b] = t;
+        }
+    }
+    int nfin = 1, nlen = 0, word = 0, par = 0;
+    float sel_v = 0.0f;
+    if (greedy_logits == nullptr) {
     float v0 = -INFINITY, v1 = -INFINITY; int i0 = 0x7fffffff, i1 = 0x7fffffff;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -235,7 +251,7 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
             if (h == 0) { v0 = tot; i0 = i; } else { v1 = tot; i1 = i; }
         }
     }
-    float sel_v = 0.0f; int sel_i = 0;
+    int sel_i = 0;
     for (int k = 0; k < W; ++k) {
         float v; int i;
         if (v0 > v1 || (v0 == v1 && i0 < i1)) { v = v0; i = i0; } else { v = v1; i = i1; }
@@ -244,7 +260,6 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
         if (i0 == i) { v0 = -INFINITY; i0 = 0x7fffffff; }
         if (i1 == i) { v1 = -INFINITY; i1 = 0x7fffffff; }
     }
-    int nfin = 1, nlen = 0, word = 0, par = 0;
     if (lane < W) {
         word = sel_i % VOCAB; par = sel_i / VOCAB;
         const int pf = fin[r0 + par];
@@ -263,6 +278,7 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
     // -inf slot, possible for widths > 7, would let dtype.min candidates of other beams in)
     const unsigned allfinite = __ballot_sync(0xffffffffu, lane >= W || sel_v > F32_MIN);
     if (lane == 0 && allfin == 0xffffffffu && allfinite == 0xffffffffu) skip[b] = 1;
+    }   // beam search
     // input of the next step's cell GEMM, gathered through the parents chosen just now: X[r] = [attention[src] | h[src]]
     // (two stacked cells: h of cell 0 comes from h0, and the top cell's h goes into the second half of X1[r] = [h0_new[r] | h1[src]])
     for (int k = 0; k < W; ++k) {
@@ -302,10 +318,11 @@ __global__ void init_state_kernel(float *lp, int32_t *fin, int32_t *len, int32_t
 
 // gather_tree on [B,S,W] arrays + T = max over snippets of (first all-finished step + 1)
 __global__ void finalize_kernel(const int32_t *step_ids, const int32_t *parent_ids, const int32_t *len, const int32_t *first_done,
-                                int32_t *ids, int32_t *steps, int B, int W, int S) {
+                                int32_t *ids, int32_t *steps, int B, int W, int S, int greedy) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= B * W) return;
     const int b = g / W, k = g % W;
+    if (greedy) { atomicMax(steps, min(first_done[b] + 1, S)); return; }      // sample ids were written step by step
     int maxlen = 0;
     for (int q = 0; q < W; ++q) maxlen = max(maxlen, len[b * W + q]);
     const int L = min(S, maxlen);
@@ -334,6 +351,7 @@ size_t workspace_floats(long long rows, int depth) {
 int run(const Params &p, cudaStream_t s) {
     if (p.B <= 0 || p.S <= 0) return RVB_OK;
     if (p.W < 1 || p.W > WMAX) return fail(RVB_ERR_ARG, "decoder_wave: beam width must be in [1,%d]", WMAX);
+    if (p.greedy && (p.W != 1 || p.logits == nullptr)) return fail(RVB_ERR_ARG, "decoder_wave: greedy search needs width 1 and a logits buffer");
     const long long rows = (long long)p.B * p.W;
     float *X = p.ws, *Z = X + rows * 256, *XA = Z + rows * 512, *Q = XA + rows * 384, *ATT = Q + rows * 256;
     float *c0 = ATT + rows * 128, *c1 = c0 + rows * 128, *lp = c1 + rows * 128;
@@ -374,13 +392,13 @@ int run(const Params &p, cudaStream_t s) {
         {
             ProfScope ps(KK_DECODER, s);
             // cell update fused into the GEMM epilogue; with fp16 weight planes both GEMMs run on the fp16 pipe (3 split passes)
-            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr, 0, 0};
+            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr, 0, 0, p.gru};
             if (two) {
                 // cell 0: h0 (fp32, for the next step's gather) -> H0, and as fp16 planes into the first half of X1;
                 // cell 1: X1 = [h0 | h1_prev[src]] . [W1 ; U1] + b1 with its own c ping-pong; its h is the query / attention-layer input
                 float *din = (t & 1) ? d1 : d0, *dout = (t & 1) ? d0 : d1;
-                const gemm::CellEpilogue ce0{p.wtok, tok, parent, cin, cout, H0, p.W, x1_hi, x1_lo, UNITS, 2 * UNITS};
-                const gemm::CellEpilogue ce1{p.b1, nullptr, parent, din, dout, XA, p.W, h_hi, h_lo, 0, 0};
+                const gemm::CellEpilogue ce0{p.wtok, tok, parent, cin, cout, H0, p.W, x1_hi, x1_lo, UNITS, 2 * UNITS, p.gru};
+                const gemm::CellEpilogue ce1{p.b1, nullptr, parent, din, dout, XA, p.W, h_hi, h_lo, 0, 0, p.gru};
                 RVB_CHECK(gemm::run_tc_f16(x_hi, x_lo, p.wg16_hi, p.wg16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce0));
                 RVB_CHECK(gemm::run_tc_f16(x1_hi, x1_lo, p.wg1_16_hi, p.wg1_16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce1));
                 RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s));
@@ -411,14 +429,15 @@ int run(const Params &p, cudaStream_t s) {
             RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
                                                 p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr,
-                                                two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr, skip);
+                                                two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr, skip,
+                                                p.greedy ? p.logits : nullptr, p.greedy ? p.ids : nullptr);
             RVB_LAUNCH_CHECK();
         }
         nl += 2;
     }
     {
         ProfScope ps(KK_DECODER, s);
-        finalize_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(p.step_ids, p.parent_ids, len, first_done, p.ids, p.steps, p.B, p.W, p.S);
+        finalize_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, s>>>(p.step_ids, p.parent_ids, len, first_done, p.ids, p.steps, p.B, p.W, p.S, p.greedy);
         RVB_LAUNCH_CHECK();
     }
     count_launch(nl + 1);

@@ -38,6 +38,7 @@ struct Params {
     int B, T;
     int precision;              // RVB_PREC_FP32: 3 split passes, RVB_PREC_BF16: single 16-bit pass
     int *abort_flag;
+    int gru;                    // 1: Keras GRUCell on the same four columns per unit (z, r, candidate input part, candidate recurrent part)
 };
 int run(int feat, const Params &p, cudaStream_t stream);
 void pack_b_image(const float *U, int rank, uint16_t *img);
@@ -61,6 +62,7 @@ struct CellEpilogue {
     int W;                      // beams per snippet (parent indices are relative to the snippet's first row)
     uint16_t *h_hi, *h_lo;      // optional fp16 hi / lo planes of h at [row*h_ld + unit]: A operand of the next GEMM
     int xa_ld, h_ld;            // row pitches in elements (0 = the depth-1 defaults 384 / 128)
+    int gru;                    // 1: GRU cell (columns z, r, candidate input part, candidate recurrent part); c_in / c_out carry h
 };
 int run_tc(const float *A, const float *WhiT, const float *WloT, const float *bias, float *C, long long M, int N, int K,
            int precision, int *abort_flag, cudaStream_t s, long long lda = 0, const CellEpilogue *cell = nullptr);
@@ -111,6 +113,9 @@ struct Params {
     const void *wg1_16_hi, *wg1_16_lo;   // decoder_depth 2: fp16 hi / lo planes of [kernel ; recurrent kernel] of cell 1, transposed [512,256]
     const float *b1;            // decoder_depth 2: bias of cell 1, [512] in [unit][gate] order
     int depth;                  // stacked decoder cells: 1 or 2
+    int gru;                    // 1: GRU cells (the weights carry the four-column form: z, r, candidate input part, candidate recurrent part)
+    int greedy;                 // 1: greedy search (W == 1): ids = sample_id [B,S], logits [B,S,7]; no beam bookkeeping
+    float *logits;              // greedy only
     const float *wfc, *bfc;     // [128][7], [7]
     int B, Tm, W, S;
     int32_t *ids;               // predicted_ids [B,S,W]

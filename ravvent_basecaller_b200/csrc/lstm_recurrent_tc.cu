@@ -100,6 +100,22 @@ __device__ __forceinline__ void lstm_pointwise2(f32x2 zi, f32x2 zf, f32x2 zg, f3
     const f32x2 Cc = add2(ex2_2(mul2(min_2(cn, 10.0f), l2)), one);
     hn = mul2(mul2(mul2(r, F), add2(Cc, mtwo)), rcp_2(Cc));   // sigmoid(zo) tanh(c') = r F (Cc - 2) / Cc
 }
+// Keras GRUCell (reset_after = True), two units at once, on the same four pre-activation columns per unit:
+//   s0 = z gate, s1 = r gate, s2 = input part of the candidate, s3 = recurrent part of the candidate (incl. its bias)
+//   z = sigmoid(s0), r = sigmoid(s1), hh = tanh(s2 + r * s3), h' = z * h + (1 - z) * hh
+// One reciprocal serves both sigmoids (Z R <= (1 + e^20)^2, finite); 3 ex2 + 2 rcp per unit.
+__device__ __forceinline__ void gru_pointwise2(f32x2 s0, f32x2 s1, f32x2 s2, f32x2 s3, f32x2 h, f32x2 &hn) {
+    constexpr float L2E = 1.4426950408889634f;
+    const f32x2 one = pk(1.0f, 1.0f), mtwo = pk(-2.0f, -2.0f), nl = pk(-L2E, -L2E), l2 = pk(2.0f * L2E, 2.0f * L2E);
+    const f32x2 Z = add2(ex2_2(mul2(max_2(s0, -20.0f), nl)), one);
+    const f32x2 R = add2(ex2_2(mul2(max_2(s1, -20.0f), nl)), one);
+    const f32x2 inv = rcp_2(mul2(Z, R));
+    const f32x2 zg = mul2(inv, R), rg = mul2(inv, Z);             // sigmoid(s0) = 1/Z, sigmoid(s1) = 1/R
+    const f32x2 pre = fma2(rg, s3, s2);
+    const f32x2 T2 = add2(ex2_2(mul2(min_2(pre, 10.0f), l2)), one);
+    const f32x2 hh = mul2(add2(T2, mtwo), rcp_2(T2));             // tanh(pre) = (T2 - 2) / T2
+    hn = fma2(zg, add2(h, mul2(hh, pk(-1.0f, -1.0f))), hh);       // hh + z (h - hh)
+}
 __device__ __forceinline__ void lstm_pointwise(float zi, float zf, float zg, float zo, float c, float &cn, float &hn) {
     f32x2 c2, h2;
     lstm_pointwise2(pk(zi, zi), pk(zf, zf), pk(zg, zg), pk(zo, zo), pk(c, c), c2, h2);
@@ -241,7 +257,7 @@ __device__ __forceinline__ void store_h8(uint32_t hi_tile, uint32_t lo_tile, int
 // written[j]: all the tensor work of step s+1 except the four blocks (i, 3) runs UNDER the epilogue of step s, and the
 // epilogue of step s+1 starts one block after the one of step s ends.  One h buffer is enough: the accumulator barrier of
 // quarter k is committed after block (3, k), the last reader of K-block k of the old h.
-template <int F, bool PRE, int NPASS>
+template <int F, bool PRE, int NPASS, bool GRU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec_tc_kernel(Params p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -369,7 +385,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                         const float4 cv = *reinterpret_cast<const float4 *>(si + UNITS + u);
                         const int ci = n * UPQ + i;
                         h0[ci] = hv.x; h0[ci + 1] = hv.y; h0[ci + 2] = hv.z; h0[ci + 3] = hv.w;
-                        c[ci] = cv.x; c[ci + 1] = cv.y; c[ci + 2] = cv.z; c[ci + 3] = cv.w;
+                        if (GRU) { c[ci] = hv.x; c[ci + 1] = hv.y; c[ci + 2] = hv.z; c[ci + 3] = hv.w; }      // GRU: the carried state is h
+                        else { c[ci] = cv.x; c[ci + 1] = cv.y; c[ci + 2] = cv.z; c[ci + 3] = cv.w; }
                     }
             }
 #pragma unroll
@@ -510,8 +527,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 for (int u = 0; u < 8; u += 2) {                 // units u, u+1 as one packed pair
                     const int ci = n * UPQ + 8 * ch + u;
                     f32x2 cn, hn;
-                    lstm_pointwise2(pk(z[4 * u + 0], z[4 * u + 4]), pk(z[4 * u + 1], z[4 * u + 5]), pk(z[4 * u + 2], z[4 * u + 6]),
-                                    pk(z[4 * u + 3], z[4 * u + 7]), pk(c[ci], c[ci + 1]), cn, hn);
+                    if (GRU) {
+                        gru_pointwise2(pk(z[4 * u + 0], z[4 * u + 4]), pk(z[4 * u + 1], z[4 * u + 5]), pk(z[4 * u + 2], z[4 * u + 6]),
+                                       pk(z[4 * u + 3], z[4 * u + 7]), pk(c[ci], c[ci + 1]), hn);
+                        cn = hn;
+                    } else
+                        lstm_pointwise2(pk(z[4 * u + 0], z[4 * u + 4]), pk(z[4 * u + 1], z[4 * u + 5]), pk(z[4 * u + 2], z[4 * u + 6]),
+                                        pk(z[4 * u + 3], z[4 * u + 7]), pk(c[ci], c[ci + 1]), cn, hn);
                     upk(cn, c[ci], c[ci + 1]);
                     upk(hn, h8[u], h8[u + 1]);
                 }
@@ -560,26 +582,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     }
 }
 
-template <int F, bool PRE, int NPASS>
+template <int F, bool PRE, int NPASS, bool GRU>
 static int launch(const Params &p, cudaStream_t stream) {
-    RVB_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<F, PRE, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    RVB_CUDA(cudaFuncSetAttribute(lstm_rec_tc_kernel<F, PRE, NPASS, GRU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const int clusters = (p.B + 2 * ROWS - 1) / (2 * ROWS) * 2;          // x 2 directions
     {
         ProfScope ps(KK_REC, stream);
-        lstm_rec_tc_kernel<F, PRE, NPASS><<<dim3((unsigned)(clusters * 2)), THREADS, SMEM, stream>>>(p);
+        lstm_rec_tc_kernel<F, PRE, NPASS, GRU><<<dim3((unsigned)(clusters * 2)), THREADS, SMEM, stream>>>(p);
     }
     RVB_LAUNCH_CHECK();
     count_launch();
     return RVB_OK;
 }
 
+template <bool GRU>
+static int run_cell(int feat, const Params &p, cudaStream_t stream) {
+    const bool full = (p.precision == RVB_PREC_FP32);
+    if (feat == 1) return full ? launch<1, false, 3, GRU>(p, stream) : launch<1, false, 1, GRU>(p, stream);
+    if (feat == 5) return full ? launch<5, false, 3, GRU>(p, stream) : launch<5, false, 1, GRU>(p, stream);
+    if (feat == 0) return full ? launch<1, true, 3, GRU>(p, stream) : launch<1, true, 1, GRU>(p, stream);
+    return fail(RVB_ERR_ARG, "lstm_rec_tc: unsupported feature count %d", feat);
+}
+
 int run(int feat, const Params &p, cudaStream_t stream) {
     if (p.B <= 0 || p.T <= 0) return RVB_OK;
-    const bool full = (p.precision == RVB_PREC_FP32);
-    if (feat == 1) return full ? launch<1, false, 3>(p, stream) : launch<1, false, 1>(p, stream);
-    if (feat == 5) return full ? launch<5, false, 3>(p, stream) : launch<5, false, 1>(p, stream);
-    if (feat == 0) return full ? launch<1, true, 3>(p, stream) : launch<1, true, 1>(p, stream);
-    return fail(RVB_ERR_ARG, "lstm_rec_tc: unsupported feature count %d", feat);
+    return p.gru ? run_cell<true>(feat, p, stream) : run_cell<false>(feat, p, stream);
 }
 
 // ---- host-side packing ---------------------------------------------------------------------------------

@@ -544,8 +544,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             const float4 tv = __ldg(tk + u);
                             const float zi = __uint_as_float(r[4 * u]) + tv.x, zf = __uint_as_float(r[4 * u + 1]) + tv.y;
                             const float zg = __uint_as_float(r[4 * u + 2]) + tv.z, zo = __uint_as_float(r[4 * u + 3]) + tv.w;
-                            cn[u] = cell_sig(zf) * cin[u] + cell_sig(zi) * cell_tanh(zg);
-                            hn[u] = cell_sig(zo) * cell_tanh(cn[u]);
+                            if (cell.gru) {          // columns: z gate, r gate, candidate input part, candidate recurrent part
+                                const float zz = cell_sig(zi), rr = cell_sig(zf), hh = cell_tanh(zg + rr * zo);
+                                hn[u] = hh + zz * (cin[u] - hh);
+                                cn[u] = hn[u];
+                            } else {
+                                cn[u] = cell_sig(zf) * cin[u] + cell_sig(zi) * cell_tanh(zg);
+                                hn[u] = cell_sig(zo) * cell_tanh(cn[u]);
+                            }
                         }
                         float4 *co = reinterpret_cast<float4 *>(cell.c_out + R * 128 + u0);
                         co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]); co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);

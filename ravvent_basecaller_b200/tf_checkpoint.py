@@ -277,6 +277,8 @@ _VAR = r"(kernel|recurrent_kernel|bias)"
 _PATTERNS = [
     (re.compile(rf"^encoder_(raw|event)/rnn_layers/(\d+)/(forward|backward)_layer/cell/{_VAR}$"),
      lambda m: f"encoder_{m[1]}/layer{m[2]}/{m[3]}/{m[4]}"),
+    # unidirectional encoders (rnn_type 'lstm' / 'gru'): tf.keras.layers.RNN(cell) without the Bidirectional wrapper
+    (re.compile(rf"^encoder_(raw|event)/rnn_layers/(\d+)/cell/{_VAR}$"), lambda m: f"encoder_{m[1]}/layer{m[2]}/forward/{m[3]}"),
     (re.compile(rf"^decoder/decoder_rnn_cell/cells/(\d+)/{_VAR}$"), lambda m: f"decoder/cell{m[1]}/{m[2]}"),
     (re.compile(rf"^decoder/rnn_cell/_cell/cells/(\d+)/{_VAR}$"), lambda m: f"decoder/cell{m[1]}/{m[2]}"),
     (re.compile(r"^decoder/attention_mechanism/memory_layer/kernel$"), lambda m: "decoder/memory_layer/kernel"),

@@ -38,21 +38,32 @@ def _lstm(rng, n_in, units):
             "bias": bias}
 
 
-def random_weights(seed=22, enc_units=128, dec_units=128, encoder_depth=2, decoder_depth=1, vocab_size=7):
+def _gru(rng, n_in, units):
+    """Keras GRUCell defaults (reset_after=True): bias [2, 3u] = (input, recurrent), gate blocks z, r, h."""
+    return {"kernel": _glorot(rng, n_in, 3 * units), "recurrent_kernel": _orthogonal(rng, units, 3 * units),
+            "bias": np.zeros((2, 3 * units), dtype=np.float32)}
+
+
+def random_weights(seed=22, enc_units=128, dec_units=128, encoder_depth=2, decoder_depth=1, vocab_size=7, rnn_type="bilstm"):
+    """rnn_type as in the reference constructor (basecaller.py:25-46, 86-89, 195): 'bi*' -> forward + backward encoder
+    weights and a 2*enc_units memory; '*lstm' / '*gru' -> the cell of the encoders and the decoder."""
     rng = np.random.default_rng(seed)
     w = {}
+    bi = "bi" in rnn_type
+    cell = _lstm if "lstm" in rnn_type else _gru
+    enc_out = (2 if bi else 1) * enc_units
     for enc, feat in (("encoder_raw", 1), ("encoder_event", 5)):
         for l in range(encoder_depth):
-            n_in = feat if l == 0 else 2 * enc_units
-            for d in ("forward", "backward"):
-                for k, v in _lstm(rng, n_in, enc_units).items():
+            n_in = feat if l == 0 else enc_out
+            for d in (("forward", "backward") if bi else ("forward",)):
+                for k, v in cell(rng, n_in, enc_units).items():
                     w[f"{enc}/layer{l}/{d}/{k}"] = v
     for j in range(decoder_depth):
         n_in = vocab_size + dec_units if j == 0 else dec_units
-        for k, v in _lstm(rng, n_in, dec_units).items():
+        for k, v in cell(rng, n_in, dec_units).items():
             w[f"decoder/cell{j}/{k}"] = v
-    w["decoder/memory_layer/kernel"] = _glorot(rng, 2 * enc_units, dec_units)
-    w["decoder/attention_layer/kernel"] = _glorot(rng, dec_units + 2 * enc_units, dec_units)
+    w["decoder/memory_layer/kernel"] = _glorot(rng, enc_out, dec_units)
+    w["decoder/attention_layer/kernel"] = _glorot(rng, dec_units + enc_out, dec_units)
     w["decoder/fc/kernel"] = _glorot(rng, dec_units, vocab_size)
     w["decoder/fc/bias"] = np.zeros(vocab_size, dtype=np.float32)
     return w

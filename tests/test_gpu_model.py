@@ -246,7 +246,7 @@ def test_projection_kernel(prec):
 def test_error_paths():
     import ravvent_basecaller_b200 as rb
     with pytest.raises(NotImplementedError):
-        rb.Basecaller(128, 128, 128, rb.nuc_tk, 'joint', 0., rnn_type='bigru')
+        rb.Basecaller(128, 128, 128, rb.nuc_tk, 'joint', 0., rnn_type='birnn')
     with pytest.raises(rb.RavventError):
         rb.Basecaller(64, 64, 128, rb.nuc_tk, 'joint', 0.)
     bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, 'raw', 0.)
