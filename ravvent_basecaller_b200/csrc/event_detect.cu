@@ -207,7 +207,24 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
     const long long raw_lo = max(0LL, ts_n0 + 1 - 2 * w2);
     const int n_raw = (int)(b - raw_lo);
 
-    for (int j = tid; j < n_raw; j += THREADS) raw_s[j] = (int)raw[raw_lo + j];
+    if (sizeof(T) == 4) {
+        // 128-bit coalesced loads: walk 16-byte aligned quads of the global array that cover [raw_lo, raw_lo + n_raw)
+        const int *g = reinterpret_cast<const int *>(p.signal);
+        const long long g_lo = base + raw_lo, g_hi = g_lo + n_raw;
+        const long long q_lo = g_lo & ~3LL;
+        for (long long qd = q_lo + 4LL * tid; qd < g_hi; qd += 4LL * THREADS) {
+            if (qd >= g_lo && qd + 4 <= g_hi) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(g + qd));
+                int *d = raw_s + (qd - g_lo);
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            } else {
+                for (int k = 0; k < 4; ++k)
+                    if (qd + k >= g_lo && qd + k < g_hi) raw_s[qd + k - g_lo] = __ldg(g + qd + k);
+            }
+        }
+    } else {
+        for (int j = tid; j < n_raw; j += THREADS) raw_s[j] = (int)raw[raw_lo + j];
+    }
     __syncthreads();
 
     // ---- phase T: t-statistics, one per (sample, window) ------------------------------------
@@ -273,9 +290,23 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
     __syncthreads();
     if (tid < nsub) {
         if (tid >= 1 && !pair_equal(sub_end[tid - 1], sub_start[tid])) atomicOr(&s_inner_bad, 1);
-        int pre = 0;
-        for (int q = 0; q < tid; ++q) pre += __popc(sub_mask[q]);
-        sub_pre[tid] = pre;
+    }
+    {
+        // exclusive prefix count of the speculative fires: warp-shuffle scan + one pass over the per-warp totals
+        __shared__ int warp_tot[THREADS / 32];
+        const int lane = tid & 31, wid = tid >> 5;
+        const int mine = (tid < nsub) ? __popc(sub_mask[tid]) : 0;
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        int off = 0;
+        for (int w = 0; w < wid; ++w) off += warp_tot[w];
+        if (tid < nsub) sub_pre[tid] = off + inc - mine;
     }
     __syncthreads();
     if (tid == 0) {
