@@ -181,6 +181,11 @@ __device__ __forceinline__ void umma_f16_2sm_lo(uint32_t d_tmem, uint32_t a_lo, 
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(IDESC), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {         // one lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -310,7 +315,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REG_IDLE));
         // ================= MMA issuer: one thread of the leader CTA drives both SMs =================
-        if (warp == 1 && rank == 0 && lane == 0) {
+        // The whole warp runs the schedule (warp-uniform control flow and descriptor arithmetic -> uniform datapath); only the
+        // tcgen05 instructions themselves are predicated on one elected lane.
+        if (warp == 1 && rank == 0) {
             // descriptors differ only in their low word (start address >> 4): keep the two bases and add immediates per
             // instruction -- hoisting all 192 descriptors out of the step loop costs more registers than this warp owns
             const uint64_t ad0 = make_desc(smem_u32(a_tiles)), bd0 = make_desc(smem_u32(b_tiles));
@@ -343,19 +350,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                     if (j > 0) {
                         if (!mbar_wait(&drained[j], s & 1, p.abort_flag)) { ok = false; break; }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (elect_one()) {
 #pragma unroll
-                        for (int i = 0; i < j; ++i) block(j, i);              // (j, 0) opens quarter j (overwrite)
+                            for (int i = 0; i < j; ++i) block(j, i);          // (j, 0) opens quarter j (overwrite)
+                        }
+                        __syncwarp();
                     }
                     if (!mbar_wait(&written[j], s & 1, p.abort_flag)) { ok = false; break; }
                     if (j == 0 && !mbar_wait(&drained[0], s & 1, p.abort_flag)) { ok = false; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
 #pragma unroll
-                    for (int i = 0; i < j; ++i) {
-                        block(i, j);
-                        if (j == NQ - 1) umma_commit_2sm(&acc_ready[i]);      // quarter i complete, K-block i of the old h free
+                        for (int i = 0; i < j; ++i) {
+                            block(i, j);
+                            if (j == NQ - 1) umma_commit_2sm(&acc_ready[i]);  // quarter i complete, K-block i of the old h free
+                        }
+                        block(j, j);
+                        if (j == NQ - 1) umma_commit_2sm(&acc_ready[j]);
                     }
-                    block(j, j);
-                    if (j == NQ - 1) umma_commit_2sm(&acc_ready[j]);
+                    __syncwarp();
                 }
             }
         }
