@@ -34,7 +34,12 @@ constexpr int HMAX = 256;
 constexpr int WMAX = 32;
 constexpr int THREADS = 256;
 constexpr int RAW_CAP = CH + HMAX + 2 * WMAX;
-constexpr int TS_CAP = CH + HMAX;
+constexpr int TS_CAP = (CH + HMAX) + (CH + HMAX) / SUB + 2;
+// The speculative walks read the staged t-statistics with a stride of SUB doubles (= 128 bytes) between the threads of a
+// warp: unpadded, all 32 lanes hit the same bank pair (ncu: 118 M shared-memory bank conflicts per launch, the whole
+// kernel's bottleneck).  One padding double per SUB entries spreads a warp's reads over 16 bank pairs.
+__device__ __forceinline__ int tsi(int j) { return j + (j >> 4); }
+static_assert(SUB == 16, "tsi() pads one double per 16 entries");
 constexpr double FLT_MIN_D = 1.17549435e-38;   // event_detector.py:10
 constexpr double FLT_MAX_D = 3.40282347e+38;   // event_detector.py:11
 
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
             t1 = tstat_general(raw, n, w1, w2);
             t2 = tstat_general(raw, n, w2, w2);
         }
-        ts1[j] = t1; ts2[j] = t2;
+        ts1[tsi(j)] = t1; ts2[tsi(j)] = t2;
     }
     __syncthreads();
 
@@ -265,14 +270,14 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
         Pair st; det_reset(st.s); det_reset(st.l);
         for (long long n = seg0 - hq + 1; n <= seg0; ++n) {
             int j = (int)(n - ts_n0 - 1);
-            pair_step(st, ts1[j], ts2[j], (uint32_t)(n - w2), p);
+            pair_step(st, ts1[tsi(j)], ts2[tsi(j)], (uint32_t)(n - w2), p);
         }
         pair_normalise(st, seg0, w2);
         sub_start[tid] = st;
         uint32_t mask = 0;
         for (long long n = seg0 + 1; n <= seg1; ++n) {
             int j = (int)(n - ts_n0 - 1);
-            if (pair_step(st, ts1[j], ts2[j], (uint32_t)(n - w2), p)) mask |= 1u << (int)(n - seg0 - 1);
+            if (pair_step(st, ts1[tsi(j)], ts2[tsi(j)], (uint32_t)(n - w2), p)) mask |= 1u << (int)(n - seg0 - 1);
         }
         pair_normalise(st, seg1, w2);
         sub_end[tid] = st;
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(THREADS) event_detect_kernel(Params p) {
                     mask = 0;
                     for (long long n = seg0 + 1; n <= seg1; ++n) {
                         int j = (int)(n - ts_n0 - 1);
-                        if (pair_step(cur, ts1[j], ts2[j], (uint32_t)(n - w2), p)) mask |= 1u << (int)(n - seg0 - 1);
+                        if (pair_step(cur, ts1[tsi(j)], ts2[tsi(j)], (uint32_t)(n - w2), p)) mask |= 1u << (int)(n - seg0 - 1);
                     }
                     pair_normalise(cur, seg1, w2);
                 }
