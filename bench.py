@@ -54,7 +54,8 @@ REC_BYTES_L0 = 512 + 4                    # per step per row per direction, raw 
 REC_BYTES_L1 = 2560                       # layer > 0: read 512 pre-gates + write 128 h (fp32)
 # dram__bytes_read+write per launch from the committed ncu --set full capture (profiles/), 9472-chunk wave
 # dram bytes of ONE launch on a 9 472-chunk wave (ncu --set full captures summarised under profiles/)
-NCU_TRAFFIC = {"recurrent_lstm": 9.71e9, "decoder": 63.7e9, "projection_gemm": 9.65e9, "attention": 1.949e9}
+NCU_TRAFFIC = {"recurrent_lstm": 9.71e9, "decoder": 63.7e9, "projection_gemm": 9.65e9, "attention": 1.951e9}
+NCU_TRAFFIC_BEAM = {"attention": 2.331e9}      # beam >= 2: attention_tc_kernel reads all Tm rows of both fp16 planes (profiles/r2c_ncu_full_dec5_digest.txt)
 
 
 def synth_chunks(rng, n):
@@ -269,10 +270,11 @@ class Timer:
                 "per_step": per_step}
 
 
-def roofline_entry(kr, ms_step, steps, peak, peak_src, precision, valid_rows):
+def roofline_entry(kr, ms_step, steps, peak, peak_src, precision, valid_rows, beam=1):
     dom = max(kr, key=lambda k: kr[k]["ms"])
+    traffic = (NCU_TRAFFIC_BEAM.get(dom) if beam >= 2 else None) or NCU_TRAFFIC.get(dom)
     return {"bound": "hbm", "achieved": kr[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kr[dom]["frac_hbm"], "traffic": NCU_TRAFFIC.get(dom) if precision == "fp32" else None, "peak_source": peak_src,
+            "frac": kr[dom]["frac_hbm"], "traffic": traffic if precision == "fp32" else None, "peak_source": peak_src,
             "kernel": dom, "share_of_step": kr[dom]["ms"] / (ms_step * steps),
             "launches": kr[dom]["launches"], "avg_launch_ms": kr[dom]["ms"] / max(1, kr[dom]["launches"]),
             "achieved_tflops": kr[dom]["tflops"], "valid_memory_rows_per_chunk": valid_rows,
@@ -311,7 +313,9 @@ def run_ours(args, rank, local_rank, world):
     if strong:
         base = "/dev/shm/rvb_bench_%s" % os.environ.get("MASTER_PORT", "0")
         if rank == 0:
-            np.lib.format.open_memmap(base + "_ids.npy", mode="w+", dtype=np.int32, shape=(total, S)).flush()
+            mm = np.lib.format.open_memmap(base + "_ids.npy", mode="w+", dtype=np.int32, shape=(total, S))
+            mm[:, 0] = -1                                   # sentinel: every row must be overwritten by the rank that owns it
+            mm.flush(); del mm
             np.lib.format.open_memmap(base + "_sc.npy", mode="w+", dtype=np.float32, shape=(total, S)).flush()
         tm.barrier()
         shm = (np.load(base + "_ids.npy", mmap_mode="r+"), np.load(base + "_sc.npy", mmap_mode="r+"))
@@ -334,10 +338,12 @@ def run_ours(args, rank, local_rank, world):
     ms1, ms_o, ms_e2e = r1["ms"], ro["ms"], re["ms"]
     gathered_ok = None
     if strong:
+        ids_chk = np.asarray(re["out"])                     # this rank's own result: its rows of the shared array must equal it
         tm.barrier()
         if rank == 0:                                       # every shard landed where its inputs were
             probe = np.linspace(0, total - 1, 64).astype(np.int64)
-            gathered_ok = bool((shm[0][probe, 0] >= 1).all() and (shm[0][probe, 0] <= 6).all())
+            gathered_ok = bool((shm[0][probe, 0] >= 0).all() and (shm[0][:, 0] >= 0).all()
+                               and np.array_equal(np.asarray(shm[0][lo:lo + 64, :ids_chk.shape[1]]), ids_chk[:64]))
 
     weak = None
     if strong and not args.no_weak:
@@ -395,13 +401,13 @@ def run_ours(args, rank, local_rank, world):
             "tflops_algorithmic": rate(ms1) * FLOP_PER_CHUNK[args.beam] / 1e12,
             "beam%d" % other: {"value": rate(ms_o) * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": ms_o,
                                "chunks_per_s": rate(ms_o), "kernels": kro,
-                               "roofline": roofline_entry(kro, ms_o, max(1, args.steps // 2), peak, peak_src, args.precision, valid_rows)},
+                               "roofline": roofline_entry(kro, ms_o, max(1, args.steps // 2), peak, peak_src, args.precision, valid_rows, other)},
             "e2e": {"value": rate(ms_e2e) * BASES_PER_CHUNK, "unit": "bases/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "host_buffers": "pageable numpy (staged through the handle's pinned ring)",
                     "gathered_in_input_order": gathered_ok},
             "gpu_launches": r1["launches"], "clocks": r1["clocks"],
-            "roofline": roofline_entry(kr, ms1, args.steps, peak, peak_src, args.precision, valid_rows),
+            "roofline": roofline_entry(kr, ms1, args.steps, peak, peak_src, args.precision, valid_rows, args.beam),
             "kernels": kr, "step_ms": r1["per_step"],
         }
         if weak:

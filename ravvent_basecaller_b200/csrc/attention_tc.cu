@@ -404,14 +404,12 @@ int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const f
     CUtensorMap mh, ml;
     RVB_CHECK(make_map3(&mh, v_hi, B, Tm));
     RVB_CHECK(make_map3(&ml, v_lo, B, Tm));
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-        RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    }
+    // per launch, not once per process: the attribute is per device, and ShardedBasecaller drives every GPU from one process
+    int dev = 0, sms = 0;
+    RVB_CUDA(cudaGetDevice(&dev));
+    RVB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const unsigned grid = (unsigned)(B < sms ? B : sms);
     if (W <= 5) attention_tc_kernel<5><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
     else attention_tc_kernel<9><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
