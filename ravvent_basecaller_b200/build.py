@@ -24,10 +24,8 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
 SOURCES = {
     "api.cu": [],
     "event_detect.cu": ["-fmad=false"],
-    "lstm_recurrent.cu": [],
     "lstm_recurrent_tc.cu": [],
     "proj_gemm.cu": [],
-    "decoder.cu": [],
     "decoder_wave.cu": [],
     "attention_tc.cu": [],
     "snippets.cu": ["-fmad=false"],

@@ -52,10 +52,8 @@ struct rvb_model {
     int device = 0, enc_depth = 2, dec_depth = 1, input_kind = RVB_INPUT_JOINT, precision = RVB_PREC_FP32;
     int wave = 9472;
     bool finalized = false;
-    bool use_tc = false;
     std::map<std::string, HostTensor> hw;
     // packed device weights
-    float *d_rec[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_pw[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_pb[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_phi[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // tf32 hi part, [N,K]
@@ -63,17 +61,14 @@ struct rvb_model {
     void *d_phi16[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};   // fp16 hi part, [N,K]
     void *d_plo16[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     int *d_abort = nullptr;
-    bool rec_tc = false;                       // recurrences on tcgen05 (lstm_recurrent_tc.cu)
     uint16_t *d_bimg[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     float *d_w0[2] = {nullptr, nullptr};
-    float *d_wg1 = nullptr, *d_b1 = nullptr;
     // wave-level beam decoder (decoder_wave.cu): tf32 hi/lo transposed weights + Keras-order token rows + workspace
     float *dw_wg[2] = {nullptr, nullptr}, *dw_wm[2] = {nullptr, nullptr}, *dw_wa[2] = {nullptr, nullptr}, *dw_wtok = nullptr, *dw_ws = nullptr;
     uint16_t *dw_wg16[2] = {nullptr, nullptr}, *dw_wm16[2] = {nullptr, nullptr}, *dw_wg1_16[2] = {nullptr, nullptr};
     float *dw_wg1[2] = {nullptr, nullptr}, *dw_b1 = nullptr;
     size_t dw_ws_rows = 0;
-    bool dec_wave = false;
-    float *d_wmem = nullptr, *d_wmemT = nullptr, *d_wg = nullptr, *d_wtok = nullptr, *d_watt = nullptr, *d_wfc = nullptr, *d_bfc = nullptr;
+    float *d_wfc = nullptr, *d_bfc = nullptr;
     // workspace for one wave
     size_t ws_raw_t = 0, ws_ev_t = 0, ws_tm = 0, ws_sw = 0;
     float *y_raw[2] = {nullptr, nullptr}, *y_ev[2] = {nullptr, nullptr};
@@ -150,14 +145,9 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     m->device = device; m->enc_depth = encoder_depth; m->dec_depth = decoder_depth;
     m->input_kind = input_kind; m->precision = precision;
     if (wave_snippets > 0) m->wave = (wave_snippets + 63) / 64 * 64;
-    const char *g = getenv("RVB_GEMM");
-    m->use_tc = gemm::tc_available() && !(g && strcmp(g, "simt") == 0);
-    const char *r = getenv("RVB_REC");
-    m->rec_tc = m->use_tc && !(r && strcmp(r, "ffma") == 0);
-    const char *dv = getenv("RVB_DECODER");
-    m->dec_wave = m->use_tc && !(dv && strcmp(dv, "persistent") == 0);
+    if (!gemm::tc_available()) { delete m; return fail(RVB_ERR_CUDA, "tcgen05 projection kernel unavailable on this device"); }
     const char *av = getenv("RVB_ATT");
-    m->att_tc = m->dec_wave && m->rec_tc && !(av && strcmp(av, "ffma") == 0);
+    m->att_tc = !(av && strcmp(av, "ffma") == 0);           // A/B switch: FFMA attention at beam widths >= 2
     *out = m;
     return RVB_OK;
 }
@@ -165,8 +155,6 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
 extern "C" int rvb_model_set_rnn(rvb_model_t *m, int bidirectional, int cell_kind) {
     if (!m) return fail(RVB_ERR_ARG, "null model");
     if (cell_kind != RVB_CELL_LSTM && cell_kind != RVB_CELL_GRU) return fail(RVB_ERR_ARG, "cell_kind must be RVB_CELL_LSTM or RVB_CELL_GRU");
-    if ((cell_kind == RVB_CELL_GRU || !bidirectional) && !(m->rec_tc && m->dec_wave))
-        return fail(RVB_ERR_STATE, "GRU / unidirectional models need the tensor-core recurrence and the wave decoder (unset RVB_REC / RVB_DECODER / RVB_GEMM)");
     m->bidir = bidirectional != 0;
     m->cell = cell_kind;
     m->finalized = false;
@@ -275,12 +263,10 @@ static int finalize_impl(rvb_model *m) {
         if (e == 1 && m->input_kind == RVB_INPUT_RAW) continue;
         for (int l = 0; l < m->enc_depth; ++l) {
             const int F = l == 0 ? enc_feat[e] : ENC_OUT;
-            const int KX = rec::kx_rows(l == 0 ? enc_feat[e] : 0);
-            std::vector<float> pack((size_t)2 * 2 * KX * 256);
             std::vector<float> wcat, bcat;
             if (l > 0) { wcat.resize((size_t)ENC_OUT * 2 * GATES); bcat.resize(2 * GATES); }
-            std::vector<uint16_t> bimg(m->rec_tc ? (size_t)4 * (rectc::B_IMAGE_BYTES / 2) : 0);
-            std::vector<float> w0(m->rec_tc && l == 0 ? (size_t)2 * rectc::W0_FLOATS_PER_DIR : 0, 0.0f);
+            std::vector<uint16_t> bimg((size_t)4 * (rectc::B_IMAGE_BYTES / 2));
+            std::vector<float> w0(l == 0 ? (size_t)2 * rectc::W0_FLOATS_PER_DIR : 0, 0.0f);
             for (int d = 0; d < 2; ++d) {
                 std::string base = std::string(enc_name[e]) + "/layer" + std::to_string(l) + "/" + dir_name[d] + "/";
                 // unidirectional encoders: no backward weights, and layers > 0 see enc_units inputs instead of 2 enc_units
@@ -290,28 +276,14 @@ static int finalize_impl(rvb_model *m) {
                 else RVB_CHECK(get_cell4(m, base, F, F, false, &c4));
                 struct { std::vector<float> &data; } Wr{c4.W}, Ur{c4.U}, Br{c4.b};
                 auto *W = &Wr, *U = &Ur, *Bv = &Br;
-                for (int r = 0; r < 2; ++r)
-                    for (int k = 0; k < KX; ++k)
-                        for (int g = 0; g < 4; ++g)
-                            for (int u = 0; u < 64; ++u) {
-                                const int col = g * UNITS + 64 * r + u;
-                                float v;
-                                if (k < UNITS) v = U->data[(size_t)k * GATES + col];
-                                else if (k < UNITS + F) v = W->data[(size_t)(k - UNITS) * GATES + col];
-                                else v = Bv->data[col];
-                                pack[(((size_t)(d * 2 + r) * KX + k) * 4 + g) * 64 + u] = v;
-                            }
                 if (l > 0) {
-                    // gate columns: Keras order (gate*128 + unit) for the FFMA recurrence, unit-major (unit*4 + gate)
-                    // for the tensor-core recurrence whose TMEM columns are laid out that way
+                    // gate columns unit-major (unit*4 + gate): the recurrence's TMEM columns are laid out that way
                     for (int k = 0; k < ENC_OUT; ++k)
-                        for (int n = 0; n < GATES; ++n) {
-                            const int col = m->rec_tc ? (n % UNITS) * 4 + n / UNITS : n;
-                            wcat[(size_t)k * 2 * GATES + d * GATES + col] = W->data[(size_t)k * GATES + n];
-                        }
-                    for (int n = 0; n < GATES; ++n) bcat[d * GATES + (m->rec_tc ? (n % UNITS) * 4 + n / UNITS : n)] = Bv->data[n];
+                        for (int n = 0; n < GATES; ++n)
+                            wcat[(size_t)k * 2 * GATES + d * GATES + (n % UNITS) * 4 + n / UNITS] = W->data[(size_t)k * GATES + n];
+                    for (int n = 0; n < GATES; ++n) bcat[d * GATES + (n % UNITS) * 4 + n / UNITS] = Bv->data[n];
                 }
-                if (m->rec_tc) {
+                {
                     for (int r = 0; r < 2; ++r)
                         rectc::pack_b_image(U->data.data(), r, bimg.data() + (size_t)(d * 2 + r) * (rectc::B_IMAGE_BYTES / 2));
                     if (l == 0) {
@@ -322,8 +294,7 @@ static int finalize_impl(rvb_model *m) {
                     }
                 }
             }
-            RVB_CHECK(upload(m, &m->d_rec[e][l], pack));
-            if (m->rec_tc) {
+            {
                 RVB_CHECK(dmalloc(m, &m->d_bimg[e][l], bimg.size()));
                 RVB_CUDA(cudaMemcpy(m->d_bimg[e][l], bimg.data(), bimg.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
                 if (l == 0) RVB_CHECK(upload(m, &m->d_w0[e], w0));
@@ -334,7 +305,7 @@ static int finalize_impl(rvb_model *m) {
                 RVB_CHECK(dmalloc(m, &m->d_phi[e][l], wcat.size()));
                 RVB_CHECK(dmalloc(m, &m->d_plo[e][l], wcat.size()));
                 RVB_CHECK(gemm::prepare_weights(m->d_pw[e][l], m->d_phi[e][l], m->d_plo[e][l], ENC_OUT, 2 * GATES, nullptr));
-                if (m->rec_tc) {
+                {
                     uint16_t *h16 = nullptr, *l16 = nullptr;
                     RVB_CHECK(dmalloc(m, &h16, wcat.size()));
                     RVB_CHECK(dmalloc(m, &l16, wcat.size()));
@@ -361,35 +332,7 @@ static int finalize_impl(rvb_model *m) {
         const HostTensor *Wm = &Wm_pad, *Wa = &Wa_pad;
         RVB_CHECK(get_w(m, "decoder/fc/kernel", UNITS, VOCAB, &Wf));
         RVB_CHECK(get_w(m, "decoder/fc/bias", VOCAB, -1, &Bf));
-        std::vector<float> wg((size_t)2 * UNITS * UNITS * 4), wtok((size_t)VOCAB * UNITS * 4);
-        for (int k = 0; k < 2 * UNITS; ++k)
-            for (int u = 0; u < UNITS; ++u)
-                for (int g = 0; g < 4; ++g)
-                    wg[((size_t)k * UNITS + u) * 4 + g] = k < UNITS ? Wd->data[(size_t)(VOCAB + k) * GATES + g * UNITS + u]
-                                                                    : Ud->data[(size_t)(k - UNITS) * GATES + g * UNITS + u];
-        for (int v = 0; v < VOCAB; ++v)
-            for (int u = 0; u < UNITS; ++u)
-                for (int g = 0; g < 4; ++g)
-                    wtok[((size_t)v * UNITS + u) * 4 + g] = Wd->data[(size_t)v * GATES + g * UNITS + u] + Bd->data[g * UNITS + u];
-        RVB_CHECK(upload(m, &m->d_wg, wg));
-        if (m->dec_depth == 2) {
-            Cell4 d1;
-            RVB_CHECK(get_cell4(m, "decoder/cell1/", UNITS, UNITS, true, &d1));
-            struct { std::vector<float> &data; } W1r{d1.W}, U1r{d1.U}, B1r{d1.b};
-            auto *W1 = &W1r, *U1 = &U1r, *B1 = &B1r;
-            std::vector<float> wg1((size_t)2 * UNITS * UNITS * 4), b1((size_t)UNITS * 4);
-            for (int k = 0; k < 2 * UNITS; ++k)
-                for (int u = 0; u < UNITS; ++u)
-                    for (int g = 0; g < 4; ++g)
-                        wg1[((size_t)k * UNITS + u) * 4 + g] = k < UNITS ? W1->data[(size_t)k * GATES + g * UNITS + u]
-                                                                         : U1->data[(size_t)(k - UNITS) * GATES + g * UNITS + u];
-            for (int u = 0; u < UNITS; ++u)
-                for (int g = 0; g < 4; ++g) b1[(size_t)u * 4 + g] = B1->data[g * UNITS + u];
-            RVB_CHECK(upload(m, &m->d_wg1, wg1));
-            RVB_CHECK(upload(m, &m->d_b1, b1));
-        }
-        RVB_CHECK(upload(m, &m->d_wtok, wtok));
-        if (m->dec_wave) {
+        {
             // [att-input rows ; U] as a [256,512] weight with gate columns in [unit][gate] order (the cell update is fused
             // into that GEMM's epilogue, which sees 32 consecutive columns = 8 whole units); W_mem^T [128,256], W_att [384,128]
             std::vector<float> wcat((size_t)2 * UNITS * GATES), wtk((size_t)VOCAB * GATES), wmT((size_t)UNITS * ENC_OUT);
@@ -434,12 +377,6 @@ static int finalize_impl(rvb_model *m) {
                 RVB_CHECK(upload(m, &m->dw_b1, b1v));
             }
         }
-        RVB_CHECK(upload(m, &m->d_wmem, Wm->data));
-        std::vector<float> wmT((size_t)UNITS * ENC_OUT);
-        for (int e = 0; e < ENC_OUT; ++e)
-            for (int d = 0; d < UNITS; ++d) wmT[(size_t)d * ENC_OUT + e] = Wm->data[(size_t)e * UNITS + d];
-        RVB_CHECK(upload(m, &m->d_wmemT, wmT));
-        RVB_CHECK(upload(m, &m->d_watt, Wa->data));
         RVB_CHECK(upload(m, &m->d_wfc, Wf->data));
         RVB_CHECK(upload(m, &m->d_bfc, Bf->data));
     }
@@ -448,12 +385,6 @@ static int finalize_impl(rvb_model *m) {
     RVB_CUDA(cudaDeviceSynchronize());
     m->finalized = true;
     return RVB_OK;
-}
-
-static int project(rvb_model *m, int e, int l, const float *A, float *C, long long M, cudaStream_t s) {
-    if (m->use_tc)
-        return gemm::run_tc(A, m->d_phi[e][l], m->d_plo[e][l], m->d_pb[e][l], C, M, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s);
-    return gemm::run_simt(A, m->d_pw[e][l], m->d_pb[e][l], C, M, 2 * GATES, ENC_OUT, s);
 }
 
 static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
@@ -477,7 +408,7 @@ static int ensure_workspace(rvb_model *m, int t_raw, int t_ev, int S, int W) {
     if ((size_t)Tm > m->ws_tm) {
         dfree(m, m->enc_out); dfree(m, m->mask);
         RVB_CHECK(dmalloc(m, &m->enc_out, wv * Tm * ENC_OUT));
-        if (m->precision == RVB_PREC_BF16 && m->rec_tc) { dfree(m, m->enc_out16); RVB_CHECK(dmalloc(m, &m->enc_out16, wv * Tm * ENC_OUT)); }
+        if (m->precision == RVB_PREC_BF16) { dfree(m, m->enc_out16); RVB_CHECK(dmalloc(m, &m->enc_out16, wv * Tm * ENC_OUT)); }
         RVB_CHECK(dmalloc(m, &m->mask, wv * Tm));
         if (m->att_tc) {
             dfree(m, m->enc_hi); dfree(m, m->enc_lo);
@@ -502,7 +433,7 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
     const int feat = e == 0 ? 1 : 5;
     float **yb = e == 0 ? m->y_raw : m->y_ev;
     float *G = e == 0 ? m->G_raw : m->G_ev;
-    for (int l = 0; l < m->enc_depth && m->rec_tc; ++l) {
+    for (int l = 0; l < m->enc_depth; ++l) {
         // tensor-core recurrence; intermediates are time-major (row = t*nb + b) so that a tile's rows of one
         // timestep are contiguous for both K2 and K3
         const bool last = (l == m->enc_depth - 1);
@@ -532,18 +463,6 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
                                        nbp * T, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s, true));
         }
         RVB_CHECK(rectc::run(l == 0 ? feat : 0, p, s));
-    }
-    for (int l = 0; l < m->enc_depth && !m->rec_tc; ++l) {
-        const bool last = (l == m->enc_depth - 1);
-        rec::Params p{};
-        p.x = x; p.G = G; p.wpack = m->d_rec[e][l];
-        p.state_in = l == 0 ? nullptr : m->st[e][(l - 1) & 1];
-        p.state_out = m->st[e][l & 1];
-        p.y = last ? out + (size_t)t_off * ENC_OUT : yb[l & 1];
-        p.y_bstride = last ? (long long)Tm * ENC_OUT : (long long)T * ENC_OUT;
-        p.B = nb; p.T = T;
-        if (l > 0) RVB_CHECK(project(m, e, l, yb[(l - 1) & 1], G, (long long)nb * T, s));
-        RVB_CHECK(rec::run(l == 0 ? feat : 0, p, s));
     }
     const long long n = (long long)nb * T;
     input_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, feat, nb, T, m->mask, Tm, t_off);
@@ -613,13 +532,11 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
         // beam widths >= 2: the attention runs on tcgen05 and reads the memory as fp16 hi / lo planes, which the last encoder
         // layer then writes INSTEAD of the fp32 rows (same bytes)
-        const bool tc_att = beam && m->dec_wave && m->att_tc && W >= 2;
+        const bool tc_att = beam && m->att_tc && W >= 2;
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s, tc_att));
-        // Wave-level decoder for every beam width (reduced-precision mode: its attention kernel streams the fp16 copy of the
-        // memory).  Greedy search keeps the persistent kernel.
-        static const bool greedy_persistent = getenv("RVB_GREEDY") && strcmp(getenv("RVB_GREEDY"), "persistent") == 0;
-        if (m->dec_wave && (beam || !greedy_persistent || m->cell == RVB_CELL_GRU)) {
+        // Wave-level decoder: every beam width, decoder depth and cell kind, and greedy search (a mode of its search kernel)
+        {
             if (!beam) W = 1;
             const size_t rows = (size_t)m->wave * W;
             if (rows > m->dw_ws_rows) {
@@ -645,24 +562,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             q.parent_ids = d_parent_ids ? d_parent_ids + (size_t)b0 * S * W : m->parent_ids;
             q.steps = d_steps; q.ws = m->dw_ws; q.abort_flag = m->d_abort;
             RVB_CHECK(decw::run(q, s));
-            continue;
         }
-        if (m->cell == RVB_CELL_GRU) return fail(RVB_ERR_STATE, "the persistent decoder kernel implements LSTM cells only");
-        dec::Params p{};
-        p.wmemT = m->d_wmemT; p.values = m->enc_out; p.values16 = m->enc_out16; p.mask = m->mask;
-        p.wg = m->d_wg; p.wtok = m->d_wtok; p.wg1 = m->d_wg1; p.b1 = m->d_b1; p.depth = m->dec_depth; p.watt = m->d_watt; p.wfc = m->d_wfc; p.bfc = m->d_bfc;
-        p.B = nb; p.Tm = Tm; p.W = W; p.S = S; p.beam = beam ? 1 : 0;
-        p.steps = d_steps;
-        if (beam) {
-            p.ids = d_ids + (size_t)b0 * S * W;
-            p.scores = d_scores + (size_t)b0 * S * W;
-            p.step_ids = d_step_ids ? d_step_ids + (size_t)b0 * S * W : m->step_ids;
-            p.parent_ids = d_parent_ids ? d_parent_ids + (size_t)b0 * S * W : m->parent_ids;
-        } else {
-            p.ids = d_ids + (size_t)b0 * S;
-            p.logits = d_logits + (size_t)b0 * S * VOCAB;
-        }
-        RVB_CHECK(dec::run(p, s));
     }
     return RVB_OK;
 }

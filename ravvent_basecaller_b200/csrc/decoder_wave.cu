@@ -1,6 +1,6 @@
-// K4 + K5, wave-level formulation for beam search (every beam width; greedy search keeps decoder.cu).
+// K4 + K5, wave-level decoder: beam search at every width and greedy search, one or two stacked LSTM / GRU cells.
 //
-// Same semantics as decoder.cu (tfa AttentionWrapper + LuongAttention + BeamSearchDecoder, reference
+// tfa AttentionWrapper + LuongAttention + BeamSearchDecoder / BasicDecoder semantics (reference
 // basecaller.py:296-315) but organised per decode step over ALL rows of a wave
 // (rows = snippets x beams, ~47 000 for a 9 472-snippet wave at beam 5), so that the dense parts run on the
 // tcgen05 projection kernel (K2, 3xTF32 = fp32 accuracy) instead of per-CTA FFMA loops that stall on L2 weight
@@ -54,7 +54,7 @@ __device__ __forceinline__ Row8 load_row8(const __half *src) {
     return r;
 }
 
-// ---- masked softmax(values . q') . values, one warp per snippet (same scheme as decoder.cu phase 2b) ----------
+// ---- masked softmax(values . q') . values, one warp per snippet, single-pass online softmax ----------
 template <int WT, typename VT>
 __global__ void __launch_bounds__(128) attention_kernel(const VT *__restrict__ values, const uint8_t *__restrict__ mask,
                                                         const float *__restrict__ Q, float *__restrict__ xa, int B, int Tm, int W,
@@ -173,6 +173,19 @@ __device__ __forceinline__ void warp_argmax(float &v, int &i) {
     }
 }
 
+// tf.math.top_k over the (at most 64) candidates of a snippet, two per lane: lane k receives the k-th best (value desc,
+// index asc), k < W.  Used by fc_search and by the standalone beam step the bit-exactness test calls.
+__device__ __forceinline__ void warp_topk(float v0, int i0, float v1, int i1, int W, int lane, float &sel_v, int &sel_i) {
+    for (int k = 0; k < W; ++k) {
+        float v; int i;
+        if (v0 > v1 || (v0 == v1 && i0 < i1)) { v = v0; i = i0; } else { v = v1; i = i1; }
+        warp_argmax(v, i);
+        if (lane == k) { sel_v = v; sel_i = i; }
+        if (i0 == i) { v0 = -INFINITY; i0 = 0x7fffffff; }
+        if (i1 == i) { v1 = -INFINITY; i1 = 0x7fffffff; }
+    }
+}
+
 // ---- logits = A . fc + b ; tfa _beam_search_step ; one warp per snippet ------------------------------------------
 __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict__ att, const float *__restrict__ wfc, const float *__restrict__ bfc,
                                                         float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent,
@@ -252,14 +265,7 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
         }
     }
     int sel_i = 0;
-    for (int k = 0; k < W; ++k) {
-        float v; int i;
-        if (v0 > v1 || (v0 == v1 && i0 < i1)) { v = v0; i = i0; } else { v = v1; i = i1; }
-        warp_argmax(v, i);
-        if (lane == k) { sel_v = v; sel_i = i; }
-        if (i0 == i) { v0 = -INFINITY; i0 = 0x7fffffff; }
-        if (i1 == i) { v1 = -INFINITY; i1 = 0x7fffffff; }
-    }
+    warp_topk(v0, i0, v1, i1, W, lane, sel_v, sel_i);
     if (lane < W) {
         word = sel_i % VOCAB; par = sel_i / VOCAB;
         const int pf = fin[r0 + par];
@@ -316,6 +322,61 @@ __global__ void init_state_kernel(float *lp, int32_t *fin, int32_t *len, int32_t
     if (k == 0) { first_done[r / W] = S; skip[r / W] = 0; }
 }
 
+// tfa.seq2seq.gather_tree for beam slot k of one snippet; element (level, slot) of the snippet is at [level * ts + slot].
+__device__ __forceinline__ void gather_tree_slot(const int32_t *step_ids, const int32_t *parent_ids, int32_t *out, size_t ts,
+                                                 int L, int T, int k) {
+    for (int tt = L; tt < T; ++tt) out[(size_t)tt * ts + k] = TOKEN_END;
+    int par = k;
+    for (int level = L - 1; level >= 0; --level) {
+        out[(size_t)level * ts + k] = step_ids[(size_t)level * ts + par];
+        par = parent_ids[(size_t)level * ts + par];
+    }
+    bool done = false;
+    for (int tt = 0; tt < L; ++tt) {
+        int32_t *o = out + (size_t)tt * ts + k;
+        if (done) *o = TOKEN_END;
+        else if (*o == TOKEN_END) done = true;
+    }
+}
+
+// K5 standalone (parity tests): one tfa _beam_search_step on log-softmaxed rows, through the same top-k as fc_search
+__global__ void beam_step_kernel(const float *slp, const float *lp, const uint8_t *fin, const long long *len, long long B, int W, int V,
+                                 int end_token, float *scores, int32_t *word, int32_t *parent, uint8_t *nfin, long long *nlen) {
+    const int lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int n_cand = W * V;
+    float v[2] = {-INFINITY, -INFINITY}; int ix[2] = {0x7fffffff, 0x7fffffff};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        if (i < n_cand) {
+            const int k = i / V, t = i % V;
+            const float sl = fin[b * W + k] ? ((t == end_token) ? 0.0f : F32_MIN) : slp[(b * W + k) * V + t];
+            v[h] = lp[b * W + k] + sl; ix[h] = i;
+        }
+    }
+    float sel_v = 0.0f; int sel_i = 0;
+    warp_topk(v[0], ix[0], v[1], ix[1], W, lane, sel_v, sel_i);
+    if (lane < W) {
+        const int wd = sel_i % V, pr = sel_i / V;
+        const bool pf = fin[b * W + pr] != 0;
+        scores[b * W + lane] = sel_v; word[b * W + lane] = wd; parent[b * W + lane] = pr;
+        nfin[b * W + lane] = (pf || wd == end_token) ? 1 : 0;
+        nlen[b * W + lane] = len[b * W + pr] + (pf ? 0 : 1);
+    }
+}
+
+// K5 standalone: gather_tree on time-major [T,B,W] arrays as tfa.seq2seq.gather_tree takes them
+__global__ void gather_tree_kernel(const int32_t *step_ids, const int32_t *parent_ids, const int32_t *max_len, int T, long long B, int W,
+                                   int32_t *out) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= B * W) return;
+    const long long b = g / W;
+    const int L = max(0, min(T, max_len[b]));
+    gather_tree_slot(step_ids + b * W, parent_ids + b * W, out + b * W, (size_t)B * W, L, T, (int)(g % W));
+}
+
 // gather_tree on [B,S,W] arrays + T = max over snippets of (first all-finished step + 1)
 __global__ void finalize_kernel(const int32_t *step_ids, const int32_t *parent_ids, const int32_t *len, const int32_t *first_done,
                                 int32_t *ids, int32_t *steps, int B, int W, int S, int greedy) {
@@ -327,18 +388,7 @@ __global__ void finalize_kernel(const int32_t *step_ids, const int32_t *parent_i
     for (int q = 0; q < W; ++q) maxlen = max(maxlen, len[b * W + q]);
     const int L = min(S, maxlen);
     const size_t o = (size_t)b * S * W;
-    for (int tt = L; tt < S; ++tt) ids[o + (size_t)tt * W + k] = TOKEN_END;
-    int par = k;
-    for (int level = L - 1; level >= 0; --level) {
-        ids[o + (size_t)level * W + k] = step_ids[o + (size_t)level * W + par];
-        par = parent_ids[o + (size_t)level * W + par];
-    }
-    bool done = false;
-    for (int tt = 0; tt < L; ++tt) {
-        int32_t *p = ids + o + (size_t)tt * W + k;
-        if (done) *p = TOKEN_END;
-        else if (*p == TOKEN_END) done = true;
-    }
+    gather_tree_slot(step_ids + o, parent_ids + o, ids + o, (size_t)W, L, S, k);
     if (k == 0) atomicMax(steps, min(first_done[b] + 1, S));
 }
 
@@ -446,3 +496,31 @@ int run(const Params &p, cudaStream_t s) {
 
 }  // namespace decw
 }  // namespace rvb
+
+using namespace rvb;
+
+extern "C" int rvb_beam_step(const float *d_slp, const float *d_lp, const uint8_t *d_fin, const int64_t *d_len,
+                             int64_t batch, int W, int V, int end_token, float *d_scores, int32_t *d_word,
+                             int32_t *d_parent, uint8_t *d_nfin, int64_t *d_nlen, void *stream) {
+    if (batch < 0 || W < 1 || W > decw::WMAX || V < 1 || W * V > 64) return fail(RVB_ERR_ARG, "beam_step: need 1 <= W*V <= 64");
+    if (batch == 0) return RVB_OK;
+    decw::beam_step_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        d_slp, d_lp, d_fin, reinterpret_cast<const long long *>(d_len), batch, W, V, end_token, d_scores, d_word,
+        d_parent, d_nfin, reinterpret_cast<long long *>(d_nlen));
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}
+
+extern "C" int rvb_gather_tree(const int32_t *d_step_ids, const int32_t *d_parent_ids, const int32_t *d_max_len,
+                               int steps, int64_t batch, int W, int end_token, int32_t *d_out, void *stream) {
+    if (batch < 0 || W < 1 || steps < 0) return fail(RVB_ERR_ARG, "gather_tree: bad shape");
+    if (end_token != TOKEN_END) return fail(RVB_ERR_ARG, "gather_tree: end_token must be %d", TOKEN_END);
+    if (batch == 0 || steps == 0) return RVB_OK;
+    const long long n = batch * W;
+    decw::gather_tree_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        d_step_ids, d_parent_ids, d_max_len, steps, batch, W, d_out);
+    RVB_LAUNCH_CHECK();
+    count_launch();
+    return RVB_OK;
+}

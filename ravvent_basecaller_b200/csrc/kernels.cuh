@@ -4,21 +4,6 @@
 
 namespace rvb {
 
-namespace rec {     // K3, lstm_recurrent.cu
-struct Params {
-    const float *x;             // [B,T,F]           (layer 0)
-    const float *G;             // [B,T,2,512]       (layer > 0)
-    const float *wpack;         // [dir][rank][KX][4][64]
-    const float *state_in;      // [B,2,2,128] (dir, h|c) or nullptr == zeros
-    float *state_out;           // [B,2,2,128]
-    float *y;                   // (b,t,dir*128+u) at y[b*y_bstride + t*256 + dir*128 + u]
-    long long y_bstride;
-    int B, T;
-};
-int run(int feat, const Params &p, cudaStream_t stream);
-int kx_rows(int feat);
-}  // namespace rec
-
 namespace rectc {   // K3 on tcgen05 (cta_group::2), lstm_recurrent_tc.cu
 struct Params {
     const float *x;             // [B,T,F] batch-major (layer 0)
@@ -73,31 +58,6 @@ int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cuda
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
                int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false, const CellEpilogue *cell = nullptr);
 }  // namespace gemm
-
-namespace dec {     // K4 + K5, decoder.cu
-struct Params {
-    const float *wmemT;     // [128][256] transposed Luong memory layer (keys are never materialised)
-    const float *values;    // [B,Tm,256]
-    const uint16_t *values16;   // optional fp16 copy of values (reduced-precision mode): halves the decode-time HBM traffic
-    const uint8_t *mask;    // [B,Tm]
-    const float *wg;        // [256][128][4]  rows 0..127: kernel rows of the attention input, 128..255: recurrent kernel
-    const float *wtok;      // [7][128][4]    kernel row of token v + bias
-    const float *wg1;       // [256][128][4]  second stacked cell: rows 0..127 kernel (input = h of cell 0), 128..255 recurrent
-    const float *b1;        // [128][4]       second stacked cell bias
-    int depth;              // decoder_depth: 1 or 2 stacked LSTM cells
-    const float *watt;      // [384][128]
-    const float *wfc;       // [128][7]
-    const float *bfc;       // [7]
-    int B, Tm, W, S, beam;  // beam == 0: greedy (W == 1)
-    int32_t *ids;           // greedy sample_id [B,S]  | beam predicted_ids [B,S,W]
-    float *logits;          // greedy rnn_output [B,S,7]
-    float *scores;          // beam scores [B,S,W]
-    int32_t *step_ids;      // beam [B,S,W]
-    int32_t *parent_ids;    // beam [B,S,W]
-    int32_t *steps;         // atomicMax of T
-};
-int run(const Params &p, cudaStream_t stream);
-}  // namespace dec
 
 namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >= 2), decoder_wave.cu
 struct Params {
