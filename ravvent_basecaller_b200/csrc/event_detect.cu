@@ -28,7 +28,7 @@ namespace rvb {
 namespace ed {
 
 constexpr int CH = 2048;
-constexpr int SUB = 16;
+constexpr int SUB = 16;        // measured: 8 (all 8 warps busy, 56 instead of 64 steps) is slower, 1.32 vs 0.98 ms
 constexpr int NSUB = CH / SUB;
 constexpr int HMAX = 256;
 constexpr int WMAX = 32;
@@ -477,7 +477,9 @@ extern "C" int rvb_event_detect(const void *d_signal, int sample_bytes, const in
     if (w1 < 1 || w2 < 1 || w1 > ed::WMAX || w2 > ed::WMAX)
         return fail(RVB_ERR_ARG, "window lengths must be in [1,%d]", ed::WMAX);
     if (n_reads < 0 || !h_read_offsets || !h_event_offsets) return fail(RVB_ERR_ARG, "bad read/event offsets");
-    if (warmup < 0) warmup = 48;
+    // default speculative warm-up: the detectors re-synchronised within 32 samples in every case measured (0 of 1 592
+    // sub-segments needed the exact re-run); shorter only costs time (the verification falls back), never exactness
+    if (warmup < 0) warmup = 32;
     if (warmup > ed::HMAX) return fail(RVB_ERR_ARG, "warmup must be <= %d", ed::HMAX);
     if (n_reads == 0) return RVB_OK;
     for (int r = 0; r < n_reads; ++r)
