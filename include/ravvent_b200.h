@@ -69,7 +69,7 @@ int         rvb_device_count(int *count);
  * d_ev_*          structure-of-arrays event table (start, length: int32 holding
  *                 the reference's u32 values; mean, stdv: float64)
  * d_ev_count      n_reads event counts
- * warmup          speculation warm-up in samples (<= 256); 48 is the default
+ * warmup          speculation warm-up in samples (<= 256); < 0 selects the default (32)
  *                 when negative.  Results never depend on it (exact verify).
  * Bit-exact vs the reference for start/length/mean; stdv differs only where
  * libm pow(mean,2) != mean*mean.
