@@ -10,12 +10,17 @@
 // (row, beam) score and is instruction bound at beam 5 (47 % of the HBM rate).  Here both contractions run on tcgen05:
 //   * the memory V is kept by K3 as fp16 hi + lo planes ([B, Tm, 256] each, the same bytes as fp32) and TMA-loaded in
 //     128-row tiles, cut into "units" of 64 KB = 128 rows x 128 columns x (hi, lo) -- a ring of three units;
-//   * scores: D_s[128 rows, 16] += V_unit (A operand, K-major: K = columns) . Q^T (B operand: beams padded to N = 16),
-//     3 split passes (V_lo.Q_hi + V_hi.Q_lo + V_hi.Q_hi) -> fp32-level accuracy on the fp16 pipe;
-//   * context: D_c[128 columns, 16] += V_unit^T (the SAME shared-memory bytes read as an MN-major A operand: M = columns,
-//     K = rows) . P (B operand written by the softmax warps as fp16 hi / lo), again 3 passes;
-//   * four softmax warps own the 128 TMEM lanes: online softmax over the (at most two) row tiles, rescaling the context
-//     accumulator in TMEM (tcgen05.ld / st) between them, normalising at the end.
+//   * scores: D_s[128 rows, .] = V_unit (A operand, K-major: K = columns) . Q^T (B operand: beams padded to 16 rows).  The
+//     three split products V_hi.Q_hi, V_hi.Q_lo, V_lo.Q_hi that give fp32-level accuracy on the fp16 pipe take TWO reads of
+//     the A operand, not three: Q_hi and Q_lo are stacked into one 32-row B operand (columns 0-15 | 16-31 of the
+//     accumulator) and V_lo meets the first 16 rows of the same tile (columns 32-47); the softmax warps add the three;
+//   * context: D_c[128 columns, .] = V_unit^T (the SAME shared-memory bytes read as an MN-major A operand: M = columns,
+//     K = rows) . P (B operand written by the softmax warps as fp16 hi / lo, stacked the same way);
+//   * an M = 128, K = 16 MMA costs ~40 cycles for any N <= 32 (tools/mma_small_n_bench.cu: it is bound by the 4 KB
+//     shared-memory read of its A operand), which is why the number of A reads is what matters;
+//   * four softmax warps own the 128 TMEM lanes: online softmax over the (at most two) row tiles.  Each tile has its own
+//     context accumulator, combined with exp(m_tile - m_final) when the snippet is written out, so no accumulator is
+//     rescaled in TMEM and tile 1's probabilities never wait for tile 0's context MMAs.
 // One persistent CTA per SM walks its snippets; warp roles: w0 TMA producer, w1 TMEM allocation + MMA issue, w2..w5 softmax.
 // Every mbarrier wait is bounded (abort flag), as in the projection kernel.
 #include "proj_gemm_tc.cuh"
@@ -38,12 +43,15 @@ constexpr int NB = 16;                          // beams padded to the smallest 
 constexpr int BOX_BYTES = ROWS * 128;           // [128 rows][64 fp16], 128-byte swizzle
 constexpr int UNIT_BYTES = 4 * BOX_BYTES;       // hi cols a | hi cols b | lo cols a | lo cols b  (128 columns of both planes)
 constexpr int RING = 3;
-constexpr int QBOX = NB * 128;                  // [16 beams][64 fp16]
-constexpr int Q_BYTES = 2 * 4 * QBOX;           // (hi | lo) x 4 K-boxes of 64 columns
-constexpr int P_BYTES = 2 * 2 * QBOX;           // (hi | lo) x 2 K-boxes of 64 rows
+constexpr int QBOX = 2 * NB * 128;              // [hi beams 0-15 | lo beams 0-15][64 fp16]: one K-box of a stacked B operand
+constexpr int LO_ROWS = NB * 128;               // byte offset of the lo rows inside a box (2 swizzle atoms of 8 rows)
+constexpr int Q_BYTES = 4 * QBOX;               // 4 K-boxes of 64 columns
+constexpr int P_TILE = 2 * QBOX;                // 2 K-boxes of 64 rows
+constexpr int P_BYTES = 2 * P_TILE;             // one per row tile: tile 1 is written while tile 0's context MMAs read theirs
 constexpr int THREADS = 192;
 constexpr size_t SMEM = 1024 + (size_t)RING * UNIT_BYTES + Q_BYTES + P_BYTES + 1024;
-constexpr int TMEM_COLS = 64;                   // scores 2 x 16 | context 2 x 16
+constexpr int ACC = 3 * NB;                     // accumulator columns per product group: hi.hi | hi.lo | lo.hi
+constexpr int TMEM_COLS = 512;                  // scores 2 tiles x 48 | context (2 tiles x 2 column halves) x 48  = 288 -> 512
 constexpr int WMAX_ = 9;                        // widest beam (decoder_wave.cu WMAX)
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
@@ -86,13 +94,6 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t (&r)[16]) {
         : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
           "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
         :: "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
 __device__ __forceinline__ void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
 __device__ __forceinline__ void split_f16(float v, uint16_t &hi, uint16_t &lo) {
@@ -164,8 +165,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_f16(ROWS, NB);                   // A, B K-major
-            constexpr uint32_t idesc_c = make_idesc_f16(ROWS, NB) | (1u << 15);      // A MN-major (V^T), B K-major
+            constexpr uint32_t idesc_s2 = make_idesc_f16(ROWS, 2 * NB), idesc_s1 = make_idesc_f16(ROWS, NB);   // A, B K-major
+            constexpr uint32_t idesc_c2 = idesc_s2 | (1u << 15), idesc_c1 = idesc_s1 | (1u << 15);             // A MN-major (V^T)
             const uint32_t q0 = smem_u32(qbuf), p0 = smem_u32(pbuf), r0 = smem_u32(ring);
             uint32_t n = 0, nq = 0, np = 0;                           // units consumed, q_ready / p_ready phases seen
             // descriptor words: low = (address >> 4) | LBO field, high = SBO | version | swizzle; one thread issues ~100 tiny MMAs
@@ -173,32 +174,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             const uint64_t dk = make_desc(0), dm = make_desc_mn(0, BOX_BYTES, 1024);
             const uint32_t k_lo = (uint32_t)dk, k_hi = (uint32_t)(dk >> 32), m_lo = (uint32_t)dm, m_hi = (uint32_t)(dm >> 32);
             const uint32_t qw = k_lo + (q0 >> 4), pw = k_lo + (p0 >> 4);
-            // scores of unit (t, h): 128 columns of K = 2 boxes x 4 k-steps, 3 split passes
+            // scores of unit (t, h): 128 columns of K = 2 boxes x 4 k-steps; V_hi . [Q_hi | Q_lo] (N = 32), V_lo . Q_hi (N = 16)
             auto scores_unit = [&](uint32_t ubase, int t, int h) {
-                const uint32_t aw = k_lo + (ubase >> 4);
+                const uint32_t aw = k_lo + (ubase >> 4), d = tmem_base + (uint32_t)(ACC * t);
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const int pa = (pass == 0) ? 1 : 0, pb = (pass == 1) ? 1 : 0;       // V_lo.Q_hi, V_hi.Q_lo, V_hi.Q_hi
+                for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_f16_w(tmem_base + 16u * (uint32_t)t, aw + (uint32_t)(((pa * 2 + jj) * BOX_BYTES + ks * 32) >> 4), k_hi,
-                                       qw + (uint32_t)((pb * (4 * QBOX) + (2 * h + jj) * QBOX + ks * 32) >> 4), k_hi, idesc_s,
-                                       (h | pass | jj | ks) ? 1u : 0u);
-                }
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t bq = qw + (uint32_t)(((2 * h + jj) * QBOX + ks * 32) >> 4);
+                        const uint32_t acc = (h | jj | ks) ? 1u : 0u;
+                        umma_f16_w(d, aw + (uint32_t)((jj * BOX_BYTES + ks * 32) >> 4), k_hi, bq, k_hi, idesc_s2, acc);
+                        umma_f16_w(d + 2 * NB, aw + (uint32_t)(((2 + jj) * BOX_BYTES + ks * 32) >> 4), k_hi, bq, k_hi, idesc_s1, acc);
+                    }
             };
-            // context of unit (t, h): columns 128h..128h+127 (M), this tile's 128 rows (K = 8 k-steps of 16), 3 split passes
+            // context of unit (t, h): columns 128h..128h+127 (M), this tile's 128 rows (K = 8 k-steps of 16), into the
+            // accumulator of (t, h): V_hi^T . [P_hi | P_lo], V_lo^T . P_hi
             auto ctx_unit = [&](uint32_t ubase, int t, int h) {
-                const uint32_t aw = m_lo + (ubase >> 4);
+                const uint32_t aw = m_lo + (ubase >> 4), d = tmem_base + (uint32_t)(2 * ACC + ACC * (2 * t + h));
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const int pa = (pass == 0) ? 1 : 0, pb = (pass == 1) ? 1 : 0;
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_f16_w(tmem_base + 32u + 16u * (uint32_t)h, aw + (uint32_t)((pa * 2 * BOX_BYTES + ks * 2048) >> 4), m_hi,
-                                   pw + (uint32_t)((pb * (2 * QBOX) + (ks >> 2) * QBOX + (ks & 3) * 32) >> 4), k_hi, idesc_c,
-                                   (t | pass | ks) ? 1u : 0u);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t bp = pw + (uint32_t)((t * P_TILE + (ks >> 2) * QBOX + (ks & 3) * 32) >> 4);
+                    umma_f16_w(d, aw + (uint32_t)((ks * 2048) >> 4), m_hi, bp, k_hi, idesc_c2, ks ? 1u : 0u);
+                    umma_f16_w(d + 2 * NB, aw + (uint32_t)((2 * BOX_BYTES + ks * 2048) >> 4), m_hi, bp, k_hi, idesc_c1, ks ? 1u : 0u);
                 }
             };
             auto wait_unit = [&](uint32_t k) -> bool { return mbar_wait(&full[k % RING], (k / RING) & 1, abort_flag); };
@@ -220,14 +217,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     scores_unit(r0 + ((nb0 + 2) % RING) * UNIT_BYTES, 1, 0);
                 }
                 for (int t = 0; t < n_tiles; ++t) {
-                    if (!mbar_wait(p_ready, np++ & 1, abort_flag)) return;       // P of tile t written (and ctx rescaled)
+                    if (!mbar_wait(p_ready, np++ & 1, abort_flag)) return;       // P of tile t written
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t k = nb0 + 2 * t + h;
                         ctx_unit(r0 + (k % RING) * UNIT_BYTES, t, h);
                         umma_commit(&empty[k % RING]);                           // unit free when these MMAs retire
                     }
-                    umma_commit(c_done);
+                    if (t == n_tiles - 1) umma_commit(c_done);                   // every context MMA of the snippet
                     if (t == 0 && n_tiles == 2) {
                         // second column half of tile 1 lands in a unit freed just now
                         if (!wait_unit(nb0 + 3)) return;
@@ -284,7 +281,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         split_f16(qv[w][half], hi, lo);
                         const uint32_t off = (uint32_t)(k >> 6) * QBOX + kmajor_off(w, k & 63);
                         sts16(q0 + off, hi);
-                        sts16(q0 + 4 * QBOX + off, lo);
+                        sts16(q0 + LO_ROWS + off, lo);
                     }
                 }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -295,9 +292,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         while (b < B && skip[b]) b += gridDim.x;
         if (b < B) write_q(b);
         for (; b < B; b = next_live(b)) {
-            float mx[WT], lsum[WT];
+            float mx[WT], lsum[WT], m0[WT];                     // running max, running sum, the max tile 0 was exponentiated against
 #pragma unroll
-            for (int w = 0; w < WT; ++w) { mx[w] = -INFINITY; lsum[w] = 0.0f; }
+            for (int w = 0; w < WT; ++w) { mx[w] = -INFINITY; lsum[w] = 0.0f; m0[w] = -INFINITY; }
             uint8_t mk[2];
 #pragma unroll
             for (int t = 0; t < 2; ++t) mk[t] = (ROWS * t + e < Tm) ? __ldg(mask + (size_t)b * Tm + ROWS * t + e) : (uint8_t)0;
@@ -305,37 +302,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                 const bool valid = mk[t] != 0;
                 if (!mbar_wait(&s_ready[t], (t == 0 ? ns0++ : ns1++) & 1, abort_flag)) return;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t r[16];
-                tmem_ld16(tlane + 16u * (uint32_t)t, r);
-                tmem_wait_ld16(r);
+                uint32_t r0[16], r1[16], r2[16];                 // V_hi.Q_hi | V_hi.Q_lo | V_lo.Q_hi
+                tmem_ld16(tlane + (uint32_t)(ACC * t), r0);
+                tmem_ld16(tlane + (uint32_t)(ACC * t + NB), r1);
+                tmem_ld16(tlane + (uint32_t)(ACC * t + 2 * NB), r2);
+                tmem_wait_ld16(r0);
+                tmem_wait_ld16(r1);
+                tmem_wait_ld16(r2);
                 float s[WT], mnew[WT];
 #pragma unroll
-                for (int w = 0; w < WT; ++w) { s[w] = valid ? __uint_as_float(r[w]) : -INFINITY; mnew[w] = s[w]; }
+                for (int w = 0; w < WT; ++w) {
+                    s[w] = valid ? (__uint_as_float(r2[w]) + __uint_as_float(r1[w])) + __uint_as_float(r0[w]) : -INFINITY;
+                    mnew[w] = s[w];
+                }
                 reduce16(mnew, true);
-                float scale[WT];
 #pragma unroll
                 for (int w = 0; w < WT; ++w) {
                     mnew[w] = fmaxf(mx[w], mnew[w]);
-                    scale[w] = (mnew[w] == -INFINITY) ? 1.0f : __expf(mx[w] - mnew[w]);     // mx = -inf, finite new max -> 0
+                    const float scale = (mnew[w] == -INFINITY) ? 1.0f : __expf(mx[w] - mnew[w]);   // mx = -inf, finite new max -> 0
                     const float pw = (s[w] == -INFINITY) ? 0.0f : __expf(s[w] - mnew[w]);
-                    lsum[w] = lsum[w] * scale[w] + pw;
+                    lsum[w] = lsum[w] * scale + pw;
                     mx[w] = mnew[w];
+                    if (t == 0) m0[w] = mnew[w];
                     s[w] = pw;
-                }
-                if (t > 0) {
-                    // context MMAs of the previous tile have retired: rescale the accumulator (thread e = column e of each half)
-                    if (!mbar_wait(c_done, nc++ & 1, abort_flag)) return;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        uint32_t c[16];
-                        tmem_ld16(tlane + 32u + 16u * (uint32_t)h, c);
-                        tmem_wait_ld16(c);
-#pragma unroll
-                        for (int w = 0; w < WT; ++w) c[w] = __float_as_uint(__uint_as_float(c[w]) * scale[w]);
-                        tmem_st16(tlane + 32u + 16u * (uint32_t)h, c);
-                    }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
                 // probabilities of this tile -> B operand of the context MMAs: P[beam w][row e], fp16 hi / lo
 #pragma unroll
@@ -343,9 +332,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     if (w < W) {
                         uint16_t hi, lo;
                         split_f16(s[w], hi, lo);
-                        const uint32_t off = (uint32_t)(e >> 6) * QBOX + kmajor_off(w, e & 63);
+                        const uint32_t off = (uint32_t)(t * P_TILE) + (uint32_t)(e >> 6) * QBOX + kmajor_off(w, e & 63);
                         sts16(p0 + off, hi);
-                        sts16(p0 + 2 * QBOX + off, lo);
+                        sts16(p0 + LO_ROWS + off, lo);
                     }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -359,19 +348,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             }
             // ---- normalise and write ctx[w, :] into the attention-layer input [h | ctx]
             reduce16(lsum, false);
+            float inv[WT], sc0[WT];                              // 1 / sum, and tile 0's exp(m_0 - m_final) (tile 1 was taken against m_final)
+#pragma unroll
+            for (int w = 0; w < WT; ++w) {
+                inv[w] = (lsum[w] > 0.0f) ? 1.0f / lsum[w] : __int_as_float(0x7fc00000);   // all masked -> NaN like tfa
+                sc0[w] = (n_tiles == 1 || m0[w] == -INFINITY) ? ((n_tiles == 1) ? 1.0f : 0.0f) : __expf(m0[w] - mx[w]);
+            }
             if (!mbar_wait(c_done, nc++ & 1, abort_flag)) return;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                uint32_t c[16];
-                tmem_ld16(tlane + 32u + 16u * (uint32_t)h, c);
-                tmem_wait_ld16(c);
+                float acc[WT];
+#pragma unroll
+                for (int w = 0; w < WT; ++w) acc[w] = 0.0f;
+                for (int t = 0; t < n_tiles; ++t) {
+                    const uint32_t col = tlane + (uint32_t)(2 * ACC + ACC * (2 * t + h));
+                    uint32_t c0[16], c1[16], c2[16];
+                    tmem_ld16(col, c0);
+                    tmem_ld16(col + NB, c1);
+                    tmem_ld16(col + 2 * NB, c2);
+                    tmem_wait_ld16(c0);
+                    tmem_wait_ld16(c1);
+                    tmem_wait_ld16(c2);
+#pragma unroll
+                    for (int w = 0; w < WT; ++w) {
+                        const float v = (__uint_as_float(c2[w]) + __uint_as_float(c1[w])) + __uint_as_float(c0[w]);
+                        acc[w] = (t == 0) ? v * sc0[w] : acc[w] + v;
+                    }
+                }
 #pragma unroll
                 for (int w = 0; w < WT; ++w)
-                    if (w < W) {
-                        const float inv = (lsum[w] > 0.0f) ? 1.0f / lsum[w] : __int_as_float(0x7fc00000);   // all masked -> NaN like tfa
-                        xa[((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e] = __uint_as_float(c[w]) * inv;
-                    }
+                    if (w < W) xa[((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e] = acc[w] * inv[w];
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
