@@ -78,6 +78,7 @@ struct rvb_model {
     uint16_t *enc_out16 = nullptr;             // fp16 copy of enc_out (reduced-precision mode only)
     uint16_t *enc_hi = nullptr, *enc_lo = nullptr;   // fp16 hi / lo planes of the memory (tcgen05 attention, beam widths >= 2)
     bool att_tc = false;
+    bool att16_tc = false;                     // reduced-precision mode: single-plane tcgen05 attention at every width
     bool bidir = true;                         // rnn_type 'bi*': Bidirectional encoders; otherwise the backward direction has zero weights (outputs exactly 0)
     int cell = RVB_CELL_LSTM;                  // LSTM or GRU cells (encoders and decoder)
     uint8_t *mask = nullptr;
@@ -148,6 +149,8 @@ extern "C" int rvb_model_create(rvb_model_t **out, int device, int enc_units, in
     if (!gemm::tc_available()) { delete m; return fail(RVB_ERR_CUDA, "tcgen05 projection kernel unavailable on this device"); }
     const char *av = getenv("RVB_ATT");
     m->att_tc = !(av && strcmp(av, "ffma") == 0);           // A/B switch: FFMA attention at beam widths >= 2
+    const char *av16 = getenv("RVB_ATT16");
+    m->att16_tc = !(av16 && strcmp(av16, "ffma") == 0);     // A/B switch: FFMA attention over the fp16 memory (reduced precision)
     *out = m;
     return RVB_OK;
 }
@@ -532,7 +535,9 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         const int nb = (int)std::min<int64_t>(m->wave, batch - b0);
         // beam widths >= 2: the attention runs on tcgen05 and reads the memory as fp16 hi / lo planes, which the last encoder
         // layer then writes INSTEAD of the fp32 rows (same bytes)
-        const bool tc_att = beam && m->att_tc && W >= 2;
+        // reduced precision: the memory is ONE fp16 plane (K3 writes it next to the fp32 rows), also read on tcgen05, at every width
+        const bool tc16 = m->precision == RVB_PREC_BF16 && m->att16_tc;
+        const bool tc_att = beam && m->att_tc && W >= 2 && !tc16;
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s, tc_att));
         // Wave-level decoder: every beam width, decoder depth and cell kind, and greedy search (a mode of its search kernel)
@@ -546,9 +551,11 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             }
             decw::Params q{};
             q.values = m->enc_out; q.mask = m->mask;
-            // fp16 copy of the memory: only at width 1, where the attention kernel is bandwidth bound (measured: at width 5 it is
-            // issue bound and the widening conversions cost more than the halved bytes save, 199 -> 251 ms per step)
-            q.values16 = (m->precision == RVB_PREC_BF16 && W == 1) ? m->enc_out16 : nullptr;
+            // fp16 copy of the memory: the tcgen05 kernel at every width; the FFMA kernel (RVB_ATT16=ffma) only at width 1, where it
+            // is bandwidth bound (measured: at width 5 it is issue bound and the widening conversions cost more than the halved
+            // bytes save, 199 -> 251 ms per step)
+            q.values16 = (m->precision == RVB_PREC_BF16 && (W == 1 || tc16)) ? m->enc_out16 : nullptr;
+            q.att16_tc = tc16 ? 1 : 0;
             q.v_hi = tc_att ? m->enc_hi : nullptr; q.v_lo = tc_att ? m->enc_lo : nullptr;
             q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
             q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];

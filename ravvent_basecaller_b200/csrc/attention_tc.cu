@@ -41,15 +41,15 @@ using gemm::tc::umma_f16;
 constexpr int ROWS = 128;                       // memory rows per tile = TMEM lanes
 constexpr int NB = 16;                          // beams padded to the smallest MMA N at M = 128
 constexpr int BOX_BYTES = ROWS * 128;           // [128 rows][64 fp16], 128-byte swizzle
-constexpr int UNIT_BYTES = 4 * BOX_BYTES;       // hi cols a | hi cols b | lo cols a | lo cols b  (128 columns of both planes)
-constexpr int RING = 3;
+constexpr int RING_BYTES = 12 * BOX_BYTES;      // 192 KB: three units of both planes, or six of one
+constexpr int MAX_RING = 6;
 constexpr int QBOX = 2 * NB * 128;              // [hi beams 0-15 | lo beams 0-15][64 fp16]: one K-box of a stacked B operand
 constexpr int LO_ROWS = NB * 128;               // byte offset of the lo rows inside a box (2 swizzle atoms of 8 rows)
 constexpr int Q_BYTES = 4 * QBOX;               // 4 K-boxes of 64 columns
 constexpr int P_TILE = 2 * QBOX;                // 2 K-boxes of 64 rows
 constexpr int P_BYTES = 2 * P_TILE;             // one per row tile: tile 1 is written while tile 0's context MMAs read theirs
 constexpr int THREADS = 192;
-constexpr size_t SMEM = 1024 + (size_t)RING * UNIT_BYTES + Q_BYTES + P_BYTES + 1024;
+constexpr size_t SMEM = 1024 + (size_t)RING_BYTES + Q_BYTES + P_BYTES + 1024;
 constexpr int ACC = 3 * NB;                     // accumulator columns per product group: hi.hi | hi.lo | lo.hi
 constexpr int TMEM_COLS = 512;                  // scores 2 tiles x 48 | context (2 tiles x 2 column halves) x 48  = 288 -> 512
 constexpr int WMAX_ = 9;                        // widest beam (decoder_wave.cu WMAX)
@@ -106,7 +106,10 @@ __device__ __forceinline__ uint32_t kmajor_off(int n, int k) {
     return (uint32_t)((n >> 3) * 1024 + (n & 7) * 128 + ((((k >> 3) ^ (n & 7)) & 7) << 4) + (k & 7) * 2);
 }
 
-template <int WT>       // beam bucket: loops over beams are unrolled to WT (5 or 9)
+// WT: beam bucket, loops over beams are unrolled to WT (1, 5 or 9).
+// PLANES: 2 = fp16 hi + lo planes of the memory (fp32-level products), 1 = one fp16 plane (the reduced-precision mode's memory:
+// half the bytes, and a whole snippet -- four 32 KB units -- fits the ring of six with room to run into the next one).
+template <int WT, int PLANES>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const uint8_t *__restrict__ mask, const float *__restrict__ Q, float *__restrict__ xa,
@@ -114,11 +117,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char *ring = smem;
-    unsigned char *qbuf = smem + (size_t)RING * UNIT_BYTES;
+    constexpr int UNIT_BYTES = 2 * PLANES * BOX_BYTES;  // hi cols a | hi cols b [| lo cols a | lo cols b]: 128 columns of every plane
+    constexpr int RING = RING_BYTES / UNIT_BYTES;
+    unsigned char *qbuf = smem + (size_t)RING_BYTES;
     unsigned char *pbuf = qbuf + Q_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(pbuf + P_BYTES);
-    uint64_t *full = bars, *empty = bars + RING;
-    uint64_t *q_ready = bars + 2 * RING, *p_ready = q_ready + 1, *c_done = q_ready + 2, *s_ready = q_ready + 3;   // s_ready[2]
+    uint64_t *full = bars, *empty = bars + MAX_RING;
+    uint64_t *q_ready = bars + 2 * MAX_RING, *p_ready = q_ready + 1, *c_done = q_ready + 2, *s_ready = q_ready + 3;   // s_ready[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(s_ready + 2);
     float *red = reinterpret_cast<float *>(tmem_slot + 2);          // [2 buffers][4 warps][16]
 
@@ -157,8 +162,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         mbar_expect_tx(&full[u], UNIT_BYTES);
                         tma_load_3d(&map_hi, &full[u], dst, 128 * h, ROWS * t, b);
                         tma_load_3d(&map_hi, &full[u], dst + BOX_BYTES, 128 * h + 64, ROWS * t, b);
-                        tma_load_3d(&map_lo, &full[u], dst + 2 * BOX_BYTES, 128 * h, ROWS * t, b);
-                        tma_load_3d(&map_lo, &full[u], dst + 3 * BOX_BYTES, 128 * h + 64, ROWS * t, b);
+                        if (PLANES == 2) {
+                            tma_load_3d(&map_lo, &full[u], dst + 2 * BOX_BYTES, 128 * h, ROWS * t, b);
+                            tma_load_3d(&map_lo, &full[u], dst + 3 * BOX_BYTES, 128 * h + 64, ROWS * t, b);
+                        }
                     }
             }
         }
@@ -184,7 +191,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         const uint32_t bq = qw + (uint32_t)(((2 * h + jj) * QBOX + ks * 32) >> 4);
                         const uint32_t acc = (h | jj | ks) ? 1u : 0u;
                         umma_f16_w(d, aw + (uint32_t)((jj * BOX_BYTES + ks * 32) >> 4), k_hi, bq, k_hi, idesc_s2, acc);
-                        umma_f16_w(d + 2 * NB, aw + (uint32_t)(((2 + jj) * BOX_BYTES + ks * 32) >> 4), k_hi, bq, k_hi, idesc_s1, acc);
+                        if (PLANES == 2)
+                            umma_f16_w(d + 2 * NB, aw + (uint32_t)(((2 + jj) * BOX_BYTES + ks * 32) >> 4), k_hi, bq, k_hi, idesc_s1, acc);
                     }
             };
             // context of unit (t, h): columns 128h..128h+127 (M), this tile's 128 rows (K = 8 k-steps of 16), into the
@@ -195,7 +203,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                 for (int ks = 0; ks < 8; ++ks) {
                     const uint32_t bp = pw + (uint32_t)((t * P_TILE + (ks >> 2) * QBOX + (ks & 3) * 32) >> 4);
                     umma_f16_w(d, aw + (uint32_t)((ks * 2048) >> 4), m_hi, bp, k_hi, idesc_c2, ks ? 1u : 0u);
-                    umma_f16_w(d + 2 * NB, aw + (uint32_t)((2 * BOX_BYTES + ks * 2048) >> 4), m_hi, bp, k_hi, idesc_c1, ks ? 1u : 0u);
+                    if (PLANES == 2)
+                        umma_f16_w(d + 2 * NB, aw + (uint32_t)((2 * BOX_BYTES + ks * 2048) >> 4), m_hi, bp, k_hi, idesc_c1, ks ? 1u : 0u);
                 }
             };
             auto wait_unit = [&](uint32_t k) -> bool { return mbar_wait(&full[k % RING], (k / RING) & 1, abort_flag); };
@@ -215,6 +224,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     if (!wait_unit(nb0 + 2)) return;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     scores_unit(r0 + ((nb0 + 2) % RING) * UNIT_BYTES, 1, 0);
+                    if (PLANES == 1) {                               // the whole snippet is in the ring
+                        if (!wait_unit(nb0 + 3)) return;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        scores_unit(r0 + ((nb0 + 3) % RING) * UNIT_BYTES, 1, 1);
+                        umma_commit(&s_ready[1]);
+                    }
                 }
                 for (int t = 0; t < n_tiles; ++t) {
                     if (!mbar_wait(p_ready, np++ & 1, abort_flag)) return;       // P of tile t written
@@ -225,7 +240,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                         umma_commit(&empty[k % RING]);                           // unit free when these MMAs retire
                     }
                     if (t == n_tiles - 1) umma_commit(c_done);                   // every context MMA of the snippet
-                    if (t == 0 && n_tiles == 2) {
+                    if (PLANES == 2 && t == 0 && n_tiles == 2) {
                         // second column half of tile 1 lands in a unit freed just now
                         if (!wait_unit(nb0 + 3)) return;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -290,29 +305,39 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         auto next_live = [&](int b) { b += gridDim.x; while (b < B && skip[b]) b += gridDim.x; return b; };
         int b = (int)blockIdx.x;
         while (b < B && skip[b]) b += gridDim.x;
-        if (b < B) write_q(b);
-        for (; b < B; b = next_live(b)) {
+        // mask bits of this thread's row in the two tiles of a snippet (bit t), fetched one snippet ahead: the load is an L2
+        // round trip that would otherwise sit in front of every snippet's first softmax
+        auto load_mask = [&](int b) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (ROWS * t + e < Tm && __ldg(mask + (size_t)b * Tm + ROWS * t + e) != 0) m |= 1u << t;
+            return m;
+        };
+        uint32_t mk = 0;
+        if (b < B) { write_q(b); mk = load_mask(b); }
+        while (b < B) {
+            const int bn = next_live(b);
             float mx[WT], lsum[WT], m0[WT];                     // running max, running sum, the max tile 0 was exponentiated against
 #pragma unroll
             for (int w = 0; w < WT; ++w) { mx[w] = -INFINITY; lsum[w] = 0.0f; m0[w] = -INFINITY; }
-            uint8_t mk[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) mk[t] = (ROWS * t + e < Tm) ? __ldg(mask + (size_t)b * Tm + ROWS * t + e) : (uint8_t)0;
             for (int t = 0; t < n_tiles; ++t) {
-                const bool valid = mk[t] != 0;
+                const bool valid = (mk >> t) & 1u;
                 if (!mbar_wait(&s_ready[t], (t == 0 ? ns0++ : ns1++) & 1, abort_flag)) return;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t r0[16], r1[16], r2[16];                 // V_hi.Q_hi | V_hi.Q_lo | V_lo.Q_hi
                 tmem_ld16(tlane + (uint32_t)(ACC * t), r0);
                 tmem_ld16(tlane + (uint32_t)(ACC * t + NB), r1);
-                tmem_ld16(tlane + (uint32_t)(ACC * t + 2 * NB), r2);
+                if (PLANES == 2) tmem_ld16(tlane + (uint32_t)(ACC * t + 2 * NB), r2);
                 tmem_wait_ld16(r0);
                 tmem_wait_ld16(r1);
-                tmem_wait_ld16(r2);
+                if (PLANES == 2) tmem_wait_ld16(r2);
                 float s[WT], mnew[WT];
 #pragma unroll
                 for (int w = 0; w < WT; ++w) {
-                    s[w] = valid ? (__uint_as_float(r2[w]) + __uint_as_float(r1[w])) + __uint_as_float(r0[w]) : -INFINITY;
+                    const float sv = (PLANES == 2) ? (__uint_as_float(r2[w]) + __uint_as_float(r1[w])) + __uint_as_float(r0[w])
+                                                   : __uint_as_float(r1[w]) + __uint_as_float(r0[w]);
+                    s[w] = valid ? sv : -INFINITY;
                     mnew[w] = s[w];
                 }
                 reduce16(mnew, true);
@@ -342,10 +367,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             }
             // The score MMAs of this snippet have retired (s_ready of its last tile was seen): the next snippet's queries can
             // go in now, so that its score MMAs are issued while this snippet's last context MMAs and output are in flight.
-            {
-                const int bn = next_live(b);
-                if (bn < B) write_q(bn);
-            }
+            uint32_t mk_next = 0;
+            if (bn < B) { write_q(bn); mk_next = load_mask(bn); }
             // ---- normalise and write ctx[w, :] into the attention-layer input [h | ctx]
             reduce16(lsum, false);
             float inv[WT], sc0[WT];                              // 1 / sum, and tile 0's exp(m_0 - m_final) (tile 1 was taken against m_final)
@@ -366,13 +389,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     uint32_t c0[16], c1[16], c2[16];
                     tmem_ld16(col, c0);
                     tmem_ld16(col + NB, c1);
-                    tmem_ld16(col + 2 * NB, c2);
+                    if (PLANES == 2) tmem_ld16(col + 2 * NB, c2);
                     tmem_wait_ld16(c0);
                     tmem_wait_ld16(c1);
-                    tmem_wait_ld16(c2);
+                    if (PLANES == 2) tmem_wait_ld16(c2);
 #pragma unroll
                     for (int w = 0; w < WT; ++w) {
-                        const float v = (__uint_as_float(c2[w]) + __uint_as_float(c1[w])) + __uint_as_float(c0[w]);
+                        const float v = (PLANES == 2) ? (__uint_as_float(c2[w]) + __uint_as_float(c1[w])) + __uint_as_float(c0[w])
+                                                      : __uint_as_float(c1[w]) + __uint_as_float(c0[w]);
                         acc[w] = (t == 0) ? v * sc0[w] : acc[w] + v;
                     }
                 }
@@ -381,6 +405,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     if (w < W) xa[((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e] = acc[w] * inv[w];
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            b = bn;
+            mk = mk_next;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -404,24 +430,35 @@ static int make_map3(CUtensorMap *map, const void *base, long long B, int Tm) {
     return RVB_OK;
 }
 
+template <int WT, int PLANES>
+static int launch(const CUtensorMap &mh, const CUtensorMap &ml, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
+                  int B, int Tm, int W, int *abort_flag, unsigned grid, cudaStream_t s) {
+    // per launch, not once per process: the attribute is per device, and ShardedBasecaller drives every GPU from one process
+    RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<WT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attention_tc_kernel<WT, PLANES><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
+    RVB_LAUNCH_CHECK();
+    return RVB_OK;
+}
+
+// v_lo == nullptr: the memory is a single fp16 plane (reduced-precision mode)
 int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
         int B, int Tm, int W, int *abort_flag, cudaStream_t s) {
     if (B <= 0) return RVB_OK;
     if (W < 1 || W > WMAX_ || Tm < 1 || Tm > 2 * ROWS) return fail(RVB_ERR_ARG, "attention_tc: unsupported width %d / memory length %d", W, Tm);
     CUtensorMap mh, ml;
     RVB_CHECK(make_map3(&mh, v_hi, B, Tm));
-    RVB_CHECK(make_map3(&ml, v_lo, B, Tm));
-    // per launch, not once per process: the attribute is per device, and ShardedBasecaller drives every GPU from one process
+    if (v_lo != nullptr) RVB_CHECK(make_map3(&ml, v_lo, B, Tm));
+    else ml = mh;
     int dev = 0, sms = 0;
     RVB_CUDA(cudaGetDevice(&dev));
     RVB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     const unsigned grid = (unsigned)(B < sms ? B : sms);
-    if (W <= 5) attention_tc_kernel<5><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
-    else attention_tc_kernel<9><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
-    RVB_LAUNCH_CHECK();
-    return RVB_OK;
+    if (v_lo != nullptr)
+        return (W <= 5) ? launch<5, 2>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s)
+                        : launch<9, 2>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s);
+    if (W == 1) return launch<1, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s);
+    return (W <= 5) ? launch<5, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s)
+                    : launch<9, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s);
 }
 
 }  // namespace atc

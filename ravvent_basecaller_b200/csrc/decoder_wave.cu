@@ -465,6 +465,8 @@ int run(const Params &p, cudaStream_t s) {
             ProfScope ps(KK_ATTENTION, s);
             if (p.v_hi != nullptr && p.W >= 2) {   // both contractions on tcgen05 (attention_tc.cu)
                 RVB_CHECK(atc::run(p.v_hi, p.v_lo, p.mask, Q, XA, skip, p.B, p.Tm, p.W, p.abort_flag, s));
+            } else if (p.values16 != nullptr && p.att16_tc) {   // reduced-precision mode: one fp16 plane, same tcgen05 kernel
+                RVB_CHECK(atc::run(p.values16, nullptr, p.mask, Q, XA, skip, p.B, p.Tm, p.W, p.abort_flag, s));
             } else if (p.values16 != nullptr) {    // reduced-precision mode: fp16 copy of the memory
                 const __half *v16 = reinterpret_cast<const __half *>(p.values16);
                 if (p.W == 1) attention_kernel<1, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);

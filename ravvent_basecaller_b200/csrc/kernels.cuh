@@ -63,6 +63,7 @@ namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >
 struct Params {
     const float *values;        // [B,Tm,256]
     const uint16_t *values16;   // optional fp16 copy of values (reduced-precision mode): the attention kernel streams it instead
+    int att16_tc;               // values16 goes through the single-plane tcgen05 attention (else the FFMA kernel)
     const uint16_t *v_hi, *v_lo;    // optional fp16 hi / lo planes of values, [B,Tm,256] each: beam widths >= 2 run the tcgen05 attention
     const uint8_t *mask;        // [B,Tm]
     const float *wg_hiT, *wg_loT;   // tf32 hi / lo of [att-input rows ; recurrent kernel], transposed [512,256], [unit][gate] columns
