@@ -267,6 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 constexpr int PTHREADS = 384;
 constexpr int PBN = 256;
 constexpr int CSTAGE_BYTES = BM * 32 * 4;       // 128 rows x 32 fp32 columns
+constexpr int CELL_TOKENS = 7;                  // rows of CellEpilogue::wtok when tok != nullptr (the decoder's vocabulary)
 
 // PAIR: 0 = independent CTAs; 1 = cluster of two, W halves TMA-multicast to both; 2 = cluster of two driving one
 // cta_group::2 MMA (M 256 = both CTAs' row tiles, each CTA holds only its half of the W stage -> 3 stages fit).
@@ -376,6 +377,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     if (PAIR) cluster_sync_pair();                   // the peer's barriers / TMEM exist before anything is sent to them
+    // Fused cell epilogue: the token rows of the input kernel (7 x N floats, or the one bias row of a stacked cell) go into the
+    // staging area the plain epilogue would use, so that the per-chunk token add is a shared-memory read instead of a
+    // dependent global load (the epilogue, not the MMA pipe, bounds this kernel).  Row pitch N + 4: rows land in different banks.
+    float *tk_s = reinterpret_cast<float *>(cstage);
+    const int tk_ld = N + 4;
+    const bool tk_smem = cell.xa != nullptr && (size_t)CELL_TOKENS * (size_t)tk_ld * 4 <= (size_t)2 * CSTAGE_BYTES;
+    if (tk_smem) {
+        const int rows = cell.tok != nullptr ? CELL_TOKENS : 1;
+        for (int i = threadIdx.x; i < rows * (N >> 2); i += PTHREADS) {
+            const int r = i / (N >> 2), c4 = i - r * (N >> 2);
+            *reinterpret_cast<float4 *>(tk_s + (size_t)r * tk_ld + 4 * c4) = __ldg(reinterpret_cast<const float4 *>(cell.wtok + (size_t)r * N) + c4);
+        }
+        __syncthreads();
+    }
 
     auto stage_a = [&](int s) { return smem + (size_t)s * cfg::STAGE_BYTES; };
     auto stage_bhi = [&](int s) { return stage_a(s) + ((NPASS == 3) ? 2 : 1) * cfg::A_BYTES; };
@@ -504,6 +519,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         for (long long tile = w_first; tile < total && ok; tile += w_step, ++it) {
             const int n_tile = (int)(tile % n_tiles); const long long m_tile = m_of(tile);
             const int as = (int)(it & 1); const long long ar = it >> 1;
+            // fused cell: what depends only on the row -- its token, the beam slot its state comes from, and the first chunk of
+            // that state -- is fetched while the accumulator is still being produced
+            const long long R = m_tile * BM + row;
+            const bool rvalid = cell.xa != nullptr && R < M;
+            int tokv = 0; long long src = 0;
+            float4 ca = make_float4(0.f, 0.f, 0.f, 0.f), cb4 = ca;
+            if (rvalid) {
+                tokv = cell.tok != nullptr ? __ldg(cell.tok + R) : 0;
+                const int Ri = (int)R;
+                src = (long long)((Ri / cell.W) * cell.W + __ldg(cell.parent + R));
+                const int u0 = (n_tile * PBN + 32 * grp) >> 2;
+                ca = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0));
+                cb4 = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0 + 4));
+            }
             if (!mbar_wait(&acc_full[as], (uint32_t)(ar & 1), abort_flag)) { ok = false; break; }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -530,18 +559,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     continue;
                 }
                 if (cell.xa != nullptr) {                  // fused LSTM cell of the wave-level decoder: 32 columns = 8 units x (i, f, g, o)
-                    const long long R = m_tile * BM + row;
-                    if (R < M) {
+                    if (rvalid) {
                         const int col0 = n_tile * PBN + c0, u0 = col0 >> 2;
-                        const float4 *tk = reinterpret_cast<const float4 *>(cell.wtok + (size_t)(cell.tok != nullptr ? __ldg(cell.tok + R) : 0) * N + col0);
-                        const long long src = (R / cell.W) * cell.W + __ldg(cell.parent + R);
-                        const float4 ca = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0));
-                        const float4 cb4 = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0 + 4));
+                        const float4 *tk = tk_smem ? reinterpret_cast<const float4 *>(tk_s + (size_t)tokv * tk_ld + col0)
+                                                   : reinterpret_cast<const float4 *>(cell.wtok + (size_t)tokv * N + col0);
                         const float cin[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
+                        if (c0 + 32 * NGRP < PBN) {        // the next chunk's state, in flight under this chunk's math
+                            ca = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0 + 8 * NGRP));
+                            cb4 = __ldg(reinterpret_cast<const float4 *>(cell.c_in + src * 128 + u0 + 8 * NGRP + 4));
+                        }
                         float cn[8], hn[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
-                            const float4 tv = __ldg(tk + u);
+                            const float4 tv = tk_smem ? tk[u] : __ldg(tk + u);
                             const float zi = __uint_as_float(r[4 * u]) + tv.x, zf = __uint_as_float(r[4 * u + 1]) + tv.y;
                             const float zg = __uint_as_float(r[4 * u + 2]) + tv.z, zo = __uint_as_float(r[4 * u + 3]) + tv.w;
                             if (cell.gru) {          // columns: z gate, r gate, candidate input part, candidate recurrent part
