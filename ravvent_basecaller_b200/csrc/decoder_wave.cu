@@ -187,6 +187,28 @@ __device__ __forceinline__ void warp_topk(float v0, int i0, float v1, int i1, in
 }
 
 // ---- logits = A . fc + b ; tfa _beam_search_step ; one warp per snippet ------------------------------------------
+// Sums over the 32 lanes of N <= 32 per-lane values at once (recursive halving: 31 shuffles instead of 5 N): afterwards
+// lane i holds the total of value i (lanes >= N hold padding).  v is used as scratch.
+template <int N>
+__device__ __forceinline__ float warp_sum_many(float (&v)[32], int lane) {
+#pragma unroll
+    for (int i = N; i < 32; ++i) v[i] = 0.0f;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            if (i < N) {                                 // pairs entirely inside the padding stay zero
+                const float keep = upper ? v[i + off] : v[i], send = upper ? v[i] : v[i + off];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+    }
+    return v[0];
+}
+
+// WT: beam bucket (1, 5 or 9), the loops over beams are unrolled to it
+template <int WT>
 __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict__ att, const float *__restrict__ wfc, const float *__restrict__ bfc,
                                                         float *lp, int32_t *fin, int32_t *len, int32_t *tok, int32_t *parent,
                                                         int32_t *first_done, float *scores, int32_t *step_ids, int32_t *parent_ids,
@@ -194,17 +216,11 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
                                                         uint16_t *__restrict__ x_hi, uint16_t *__restrict__ x_lo,
                                                         const float *__restrict__ h0, uint16_t *__restrict__ x1_hi, uint16_t *__restrict__ x1_lo,
                                                         int32_t *__restrict__ skip, float *__restrict__ greedy_logits, int32_t *__restrict__ greedy_ids) {
-    __shared__ float a_s[4][WMAX * UNITS];
     __shared__ float lg_s[4][WMAX * 8];
-    __shared__ float wfc_s[UNITS * VOCAB];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < UNITS * VOCAB; i += blockDim.x) wfc_s[i] = wfc[i];
     const int b = blockIdx.x * 4 + wid;
     const bool active = b < B;
     const bool skipped = active && skip[b] != 0;
-    if (active && !skipped)
-        for (int i = lane; i < W * UNITS; i += 32) a_s[wid][i] = att[(size_t)b * W * UNITS + i];
-    __syncthreads();
     if (!active) return;
     if (skipped) {
         // All W beams finished with finite scores: every candidate other than (beam k, end token) costs dtype.min, so tfa's
@@ -216,12 +232,42 @@ __global__ void __launch_bounds__(128) fc_search_kernel(const float *__restrict_
         }
         return;
     }
-    for (int i = lane; i < W * VOCAB; i += 32) {
-        const int k = i / VOCAB, v = i % VOCAB;
-        float a = bfc[v];
-#pragma unroll 8
-        for (int d = 0; d < UNITS; ++d) a = fmaf(a_s[wid][k * UNITS + d], wfc_s[d * VOCAB + v], a);
-        lg_s[wid][k * 8 + v] = a;
+    {
+        // output layer: lane l owns features 4 l .. 4 l + 3 of every beam's attention vector (one coalesced float4 per row) and
+        // the matching 4 x 7 block of the kernel; the W x 7 partial dot products are then summed over the lanes together
+        float wr[4][VOCAB];
+        {
+            float wflat[4 * VOCAB];
+#pragma unroll
+            for (int j = 0; j < VOCAB; ++j) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(wfc + 4 * VOCAB * lane) + j);
+                wflat[4 * j] = q.x; wflat[4 * j + 1] = q.y; wflat[4 * j + 2] = q.z; wflat[4 * j + 3] = q.w;
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+#pragma unroll
+                for (int v = 0; v < VOCAB; ++v) wr[d][v] = wflat[d * VOCAB + v];
+        }
+        constexpr int NV = WT * VOCAB;                   // 7, 35 or 63 values
+        float pa[32], pb[32];
+#pragma unroll
+        for (int k = 0; k < WT; ++k) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < W) a = __ldg(reinterpret_cast<const float4 *>(att + ((size_t)b * W + k) * UNITS) + lane);
+#pragma unroll
+            for (int v = 0; v < VOCAB; ++v) {
+                const float t4 = fmaf(a.w, wr[3][v], fmaf(a.z, wr[2][v], fmaf(a.y, wr[1][v], a.x * wr[0][v])));
+                const int i = k * VOCAB + v;
+                if (i < 32) pa[i] = t4; else pb[i - 32] = t4;
+            }
+        }
+        const float sa = warp_sum_many<(NV < 32 ? NV : 32)>(pa, lane);
+        if (lane < NV && lane < W * VOCAB) lg_s[wid][(lane / VOCAB) * 8 + lane % VOCAB] = sa + __ldg(bfc + lane % VOCAB);
+        if (NV > 32) {
+            const float sb = warp_sum_many<(NV > 32 ? NV - 32 : 1)>(pb, lane);
+            const int i = lane + 32;
+            if (i < NV && i < W * VOCAB) lg_s[wid][(i / VOCAB) * 8 + i % VOCAB] = sb + __ldg(bfc + i % VOCAB);
+        }
     }
     __syncwarp();
     const int n_cand = W * VOCAB;
@@ -479,10 +525,11 @@ int run(const Params &p, cudaStream_t s) {
         {
             ProfScope ps(KK_DECODER, s);
             RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
-            fc_search_kernel<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
-                                                p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr,
-                                                two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr, skip,
-                                                p.greedy ? p.logits : nullptr, p.greedy ? p.ids : nullptr);
+            auto fcs = (p.W == 1) ? fc_search_kernel<1> : (p.W <= 5) ? fc_search_kernel<5> : fc_search_kernel<9>;
+            fcs<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
+                                   p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr,
+                                   two ? H0 : nullptr, two ? x1_hi : nullptr, two ? x1_lo : nullptr, skip,
+                                   p.greedy ? p.logits : nullptr, p.greedy ? p.ids : nullptr);
             RVB_LAUNCH_CHECK();
         }
         nl += 2;
