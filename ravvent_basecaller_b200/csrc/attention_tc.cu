@@ -1,5 +1,5 @@
-// K4 attention on the 5th-generation tensor cores, for beam widths >= 2 (decoder_wave.cu keeps the FFMA kernel for width 1,
-// which is HBM bound there).
+// K4 attention on the 5th-generation tensor cores: beam widths >= 2 in parity mode (decoder_wave.cu keeps the FFMA kernel for
+// width 1, which runs at the HBM rate there), every width in reduced-precision mode (one fp16 plane, PLANES = 1 below).
 //
 // Replaces, per decode step, tfa LuongAttention + the context reduction of AttentionWrapper (reference basecaller.py:117-134,
 // SURVEY A.3 / A.3b) for all beams of a snippet at once:

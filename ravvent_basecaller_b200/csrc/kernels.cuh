@@ -90,7 +90,8 @@ size_t workspace_floats(long long rows, int depth = 1);
 int run(const Params &p, cudaStream_t stream);
 }  // namespace decw
 
-namespace atc {     // K4 attention on tcgen05 for beam widths >= 2, attention_tc.cu
+namespace atc {     // K4 attention on tcgen05, attention_tc.cu: fp16 hi + lo planes (parity mode, widths >= 2), or v_lo == nullptr:
+                    // one fp16 plane (reduced-precision mode, every width)
 int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
         int B, int Tm, int W, int *abort_flag, cudaStream_t s);
 }  // namespace atc
