@@ -66,6 +66,7 @@ struct rvb_model {
     // wave-level beam decoder (decoder_wave.cu): tf32 hi/lo transposed weights + Keras-order token rows + workspace
     float *dw_wg[2] = {nullptr, nullptr}, *dw_wm[2] = {nullptr, nullptr}, *dw_wa[2] = {nullptr, nullptr}, *dw_wtok = nullptr, *dw_ws = nullptr;
     uint16_t *dw_wg16[2] = {nullptr, nullptr}, *dw_wm16[2] = {nullptr, nullptr}, *dw_wg1_16[2] = {nullptr, nullptr};
+    uint16_t *dw_wa16[2] = {nullptr, nullptr};   // attention layer zero-padded to 256 output columns, fp16 hi / lo planes, transposed [256,384]
     float *dw_wg1[2] = {nullptr, nullptr}, *dw_b1 = nullptr;
     size_t dw_ws_rows = 0;
     float *d_wfc = nullptr, *d_bfc = nullptr;
@@ -364,6 +365,15 @@ static int finalize_impl(rvb_model *m) {
             RVB_CHECK(prep(wcat, 2 * UNITS, GATES, m->dw_wg, m->dw_wg16));
             RVB_CHECK(prep(wmT, UNITS, ENC_OUT, m->dw_wm, m->dw_wm16));
             RVB_CHECK(prep(Wa->data, UNITS + ENC_OUT, UNITS, m->dw_wa));
+            {   // the same layer for the fp16-plane GEMM, whose column tile is 256 wide: columns 128..255 are zero and never stored
+                std::vector<float> wa_pad((size_t)(UNITS + ENC_OUT) * 2 * UNITS, 0.0f);
+                for (int k = 0; k < UNITS + ENC_OUT; ++k)
+                    for (int n = 0; n < UNITS; ++n) wa_pad[(size_t)k * 2 * UNITS + n] = Wa->data[(size_t)k * UNITS + n];
+                RVB_CHECK(upload(m, &tmp, wa_pad));
+                RVB_CHECK(dmalloc(m, &m->dw_wa16[0], wa_pad.size()));
+                RVB_CHECK(dmalloc(m, &m->dw_wa16[1], wa_pad.size()));
+                RVB_CHECK(gemm::prepare_weights_f16(tmp, m->dw_wa16[0], m->dw_wa16[1], UNITS + ENC_OUT, 2 * UNITS, nullptr));
+            }
             RVB_CHECK(upload(m, &m->dw_wtok, wtk));
             if (m->dec_depth == 2) {
                 // second stacked cell: [kernel (input = h of cell 0) ; recurrent kernel] as one [256,512] weight, [unit][gate] columns
@@ -559,7 +569,7 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
             q.v_hi = tc_att ? m->enc_hi : nullptr; q.v_lo = tc_att ? m->enc_lo : nullptr;
             q.wg_hiT = m->dw_wg[0]; q.wg_loT = m->dw_wg[1]; q.wm_hiT = m->dw_wm[0]; q.wm_loT = m->dw_wm[1];
             q.wa_hiT = m->dw_wa[0]; q.wa_loT = m->dw_wa[1];
-            q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
+            q.wg16_hi = m->dw_wg16[0]; q.wg16_lo = m->dw_wg16[1]; q.wm16_hi = m->dw_wm16[0]; q.wm16_lo = m->dw_wm16[1]; q.wa16_hi = m->dw_wa16[0]; q.wa16_lo = m->dw_wa16[1]; q.wtok = m->dw_wtok; q.wfc = m->d_wfc; q.bfc = m->d_bfc;
             q.wg1_16_hi = m->dw_wg1_16[0]; q.wg1_16_lo = m->dw_wg1_16[1]; q.b1 = m->dw_b1; q.depth = m->dec_depth;
             q.gru = m->cell == RVB_CELL_GRU; q.greedy = beam ? 0 : 1;
             q.logits = beam ? nullptr : d_logits + (size_t)b0 * S * VOCAB;

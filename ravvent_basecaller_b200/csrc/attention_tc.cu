@@ -113,7 +113,8 @@ template <int WT, int PLANES>
 __global__ void __launch_bounds__(THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const uint8_t *__restrict__ mask, const float *__restrict__ Q, float *__restrict__ xa,
-                    const int32_t *__restrict__ skip, int B, int Tm, int W, int *abort_flag) {
+                    const int32_t *__restrict__ skip, int B, int Tm, int W, int *abort_flag,
+                    uint16_t *__restrict__ xp_hi, uint16_t *__restrict__ xp_lo) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     unsigned char *ring = smem;
@@ -402,7 +403,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                 }
 #pragma unroll
                 for (int w = 0; w < WT; ++w)
-                    if (w < W) xa[((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e] = acc[w] * inv[w];
+                    if (w < W) {
+                        const size_t o = ((size_t)b * W + w) * (3 * UNITS) + UNITS + 128 * h + e;
+                        const float v = acc[w] * inv[w];
+                        if (xp_hi != nullptr) {      // fp16 hi / lo planes of [h | ctx]: A operand of the attention-layer GEMM
+                            uint16_t hi, lo;
+                            split_f16(v, hi, lo);
+                            xp_hi[o] = hi; xp_lo[o] = lo;
+                        } else xa[o] = v;
+                    }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             b = bn;
@@ -432,17 +441,17 @@ static int make_map3(CUtensorMap *map, const void *base, long long B, int Tm) {
 
 template <int WT, int PLANES>
 static int launch(const CUtensorMap &mh, const CUtensorMap &ml, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
-                  int B, int Tm, int W, int *abort_flag, unsigned grid, cudaStream_t s) {
+                  int B, int Tm, int W, int *abort_flag, unsigned grid, cudaStream_t s, uint16_t *xp_hi, uint16_t *xp_lo) {
     // per launch, not once per process: the attribute is per device, and ShardedBasecaller drives every GPU from one process
     RVB_CUDA(cudaFuncSetAttribute(attention_tc_kernel<WT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attention_tc_kernel<WT, PLANES><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag);
+    attention_tc_kernel<WT, PLANES><<<grid, THREADS, SMEM, s>>>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, xp_hi, xp_lo);
     RVB_LAUNCH_CHECK();
     return RVB_OK;
 }
 
 // v_lo == nullptr: the memory is a single fp16 plane (reduced-precision mode)
 int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
-        int B, int Tm, int W, int *abort_flag, cudaStream_t s) {
+        int B, int Tm, int W, int *abort_flag, cudaStream_t s, uint16_t *xp_hi, uint16_t *xp_lo) {
     if (B <= 0) return RVB_OK;
     if (W < 1 || W > WMAX_ || Tm < 1 || Tm > 2 * ROWS) return fail(RVB_ERR_ARG, "attention_tc: unsupported width %d / memory length %d", W, Tm);
     CUtensorMap mh, ml;
@@ -454,11 +463,11 @@ int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const f
     RVB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const unsigned grid = (unsigned)(B < sms ? B : sms);
     if (v_lo != nullptr)
-        return (W <= 5) ? launch<5, 2>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s)
-                        : launch<9, 2>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s);
-    if (W == 1) return launch<1, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s);
-    return (W <= 5) ? launch<5, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s)
-                    : launch<9, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s);
+        return (W <= 5) ? launch<5, 2>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s, xp_hi, xp_lo)
+                        : launch<9, 2>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s, xp_hi, xp_lo);
+    if (W == 1) return launch<1, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s, xp_hi, xp_lo);
+    return (W <= 5) ? launch<5, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s, xp_hi, xp_lo)
+                    : launch<9, 1>(mh, ml, mask, Q, xa, skip, B, Tm, W, abort_flag, grid, s, xp_hi, xp_lo);
 }
 
 }  // namespace atc

@@ -58,7 +58,7 @@ __device__ __forceinline__ Row8 load_row8(const __half *src) {
 template <int WT, typename VT>
 __global__ void __launch_bounds__(128) attention_kernel(const VT *__restrict__ values, const uint8_t *__restrict__ mask,
                                                         const float *__restrict__ Q, float *__restrict__ xa, int B, int Tm, int W,
-                                                        const int32_t *__restrict__ skip) {
+                                                        const int32_t *__restrict__ skip, uint16_t *__restrict__ xp_hi, uint16_t *__restrict__ xp_lo) {
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -158,8 +158,23 @@ __global__ void __launch_bounds__(128) attention_kernel(const VT *__restrict__ v
             float v[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) unpack2(acc[w][e], v[2 * e], v[2 * e + 1]);
-            *reinterpret_cast<float4 *>(o + 4 * lane) = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
-            *reinterpret_cast<float4 *>(o + UNITS + 4 * lane) = make_float4(v[4] * inv, v[5] * inv, v[6] * inv, v[7] * inv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= inv;
+            if (xp_hi != nullptr) {      // [h | ctx] as fp16 hi / lo planes: A operand of the attention-layer GEMM (the fp32 copy is not read then)
+                const size_t po = ((size_t)b * W + w) * (3 * UNITS) + UNITS + 4 * lane;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const float *q = v + 4 * half;
+                    const __half2 h0 = __floats2half2_rn(q[0], q[1]), h1 = __floats2half2_rn(q[2], q[3]);
+                    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+                    const __half2 l0 = __floats2half2_rn(q[0] - f0.x, q[1] - f0.y), l1 = __floats2half2_rn(q[2] - f1.x, q[3] - f1.y);
+                    *reinterpret_cast<uint2 *>(xp_hi + po + UNITS * half) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                    *reinterpret_cast<uint2 *>(xp_lo + po + UNITS * half) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                }
+            } else {
+                *reinterpret_cast<float4 *>(o + 4 * lane) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(o + UNITS + 4 * lane) = make_float4(v[4], v[5], v[6], v[7]);
+            }
         }
 }
 
@@ -465,7 +480,14 @@ int run(const Params &p, cudaStream_t s) {
     if (two && (!f16 || p.wg1_16_hi == nullptr || p.b1 == nullptr))
         return fail(RVB_ERR_STATE, "decoder_wave: decoder_depth 2 needs the fp16-plane weights");
     uint16_t *x_hi = reinterpret_cast<uint16_t *>(X), *x_lo = x_hi + rows * 256;
-    uint16_t *h_hi = reinterpret_cast<uint16_t *>(Z), *h_lo = h_hi + rows * 128;
+    // [h | ctx] as fp16 hi / lo planes, [rows][384] halves each, in the Z region (the fused cell epilogue never writes Z itself):
+    // h from the cell epilogue (A operand of the query GEMM, K = 128, row pitch 384), ctx from the attention kernel, and the
+    // whole row is the A operand of the attention-layer GEMM.  Without wa16 planes only the h part is used.
+    static const bool xap_off = getenv("RVB_ATT_LAYER") && strcmp(getenv("RVB_ATT_LAYER"), "tf32") == 0;      // A/B switch
+    const bool xap = f16 && p.wa16_hi != nullptr && !xap_off;
+    const int h_ld = xap ? 3 * UNITS : UNITS;
+    uint16_t *h_hi = reinterpret_cast<uint16_t *>(Z), *h_lo = h_hi + rows * h_ld;
+    uint16_t *xp_hi = xap ? h_hi : nullptr, *xp_lo = xap ? h_lo : nullptr;
     RVB_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * rows * 256, s));          // step 0: attention = h = 0
     RVB_CUDA(cudaMemsetAsync(XA, 0, sizeof(float) * rows * 384, s));
     RVB_CUDA(cudaMemsetAsync(ATT, 0, sizeof(float) * rows * 128, s));
@@ -488,20 +510,20 @@ int run(const Params &p, cudaStream_t s) {
         {
             ProfScope ps(KK_DECODER, s);
             // cell update fused into the GEMM epilogue; with fp16 weight planes both GEMMs run on the fp16 pipe (3 split passes)
-            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr, 0, 0, p.gru};
+            const gemm::CellEpilogue ce{p.wtok, tok, parent, cin, cout, XA, p.W, f16 ? h_hi : nullptr, f16 ? h_lo : nullptr, 0, h_ld, p.gru};
             if (two) {
                 // cell 0: h0 (fp32, for the next step's gather) -> H0, and as fp16 planes into the first half of X1;
                 // cell 1: X1 = [h0 | h1_prev[src]] . [W1 ; U1] + b1 with its own c ping-pong; its h is the query / attention-layer input
                 float *din = (t & 1) ? d1 : d0, *dout = (t & 1) ? d0 : d1;
                 const gemm::CellEpilogue ce0{p.wtok, tok, parent, cin, cout, H0, p.W, x1_hi, x1_lo, UNITS, 2 * UNITS, p.gru};
-                const gemm::CellEpilogue ce1{p.b1, nullptr, parent, din, dout, XA, p.W, h_hi, h_lo, 0, 0, p.gru};
+                const gemm::CellEpilogue ce1{p.b1, nullptr, parent, din, dout, XA, p.W, h_hi, h_lo, 0, h_ld, p.gru};
                 RVB_CHECK(gemm::run_tc_f16(x_hi, x_lo, p.wg16_hi, p.wg16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce0));
                 RVB_CHECK(gemm::run_tc_f16(x1_hi, x1_lo, p.wg1_16_hi, p.wg1_16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce1));
-                RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s));
+                RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, false, nullptr, h_ld));
                 ++nl;
             } else if (f16) {
                 RVB_CHECK(gemm::run_tc_f16(x_hi, x_lo, p.wg16_hi, p.wg16_lo, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, false, &ce));
-                RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s));
+                RVB_CHECK(gemm::run_tc_f16(h_hi, h_lo, p.wm16_hi, p.wm16_lo, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, false, nullptr, h_ld));
             } else {
                 RVB_CHECK(gemm::run_tc(X, p.wg_hiT, p.wg_loT, nullptr, Z, rows, GATES, 2 * UNITS, RVB_PREC_FP32, p.abort_flag, s, 0, &ce));
                 RVB_CHECK(gemm::run_tc(XA, p.wm_hiT, p.wm_loT, nullptr, Q, rows, ENC_OUT, UNITS, RVB_PREC_FP32, p.abort_flag, s, 3 * UNITS));
@@ -510,21 +532,24 @@ int run(const Params &p, cudaStream_t s) {
         {
             ProfScope ps(KK_ATTENTION, s);
             if (p.v_hi != nullptr && p.W >= 2) {   // both contractions on tcgen05 (attention_tc.cu)
-                RVB_CHECK(atc::run(p.v_hi, p.v_lo, p.mask, Q, XA, skip, p.B, p.Tm, p.W, p.abort_flag, s));
+                RVB_CHECK(atc::run(p.v_hi, p.v_lo, p.mask, Q, XA, skip, p.B, p.Tm, p.W, p.abort_flag, s, xp_hi, xp_lo));
             } else if (p.values16 != nullptr && p.att16_tc) {   // reduced-precision mode: one fp16 plane, same tcgen05 kernel
-                RVB_CHECK(atc::run(p.values16, nullptr, p.mask, Q, XA, skip, p.B, p.Tm, p.W, p.abort_flag, s));
+                RVB_CHECK(atc::run(p.values16, nullptr, p.mask, Q, XA, skip, p.B, p.Tm, p.W, p.abort_flag, s, xp_hi, xp_lo));
             } else if (p.values16 != nullptr) {    // reduced-precision mode: fp16 copy of the memory
                 const __half *v16 = reinterpret_cast<const __half *>(p.values16);
-                if (p.W == 1) attention_kernel<1, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-                else if (p.W <= 5) attention_kernel<5, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-                else attention_kernel<9, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-            } else if (p.W == 1) attention_kernel<1, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-            else if (p.W <= 5) attention_kernel<5, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
-            else attention_kernel<9, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip);
+                if (p.W == 1) attention_kernel<1, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip, xp_hi, xp_lo);
+                else if (p.W <= 5) attention_kernel<5, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip, xp_hi, xp_lo);
+                else attention_kernel<9, __half><<<ab, 128, 0, s>>>(v16, p.mask, Q, XA, p.B, p.Tm, p.W, skip, xp_hi, xp_lo);
+            } else if (p.W == 1) attention_kernel<1, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip, xp_hi, xp_lo);
+            else if (p.W <= 5) attention_kernel<5, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip, xp_hi, xp_lo);
+            else attention_kernel<9, float><<<ab, 128, 0, s>>>(p.values, p.mask, Q, XA, p.B, p.Tm, p.W, skip, xp_hi, xp_lo);
         }
         {
             ProfScope ps(KK_DECODER, s);
-            RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
+            if (xap)        // [h | ctx] planes x the attention layer padded to one 256-column tile; 128 columns come out
+                RVB_CHECK(gemm::run_tc_f16(xp_hi, xp_lo, p.wa16_hi, p.wa16_lo, nullptr, ATT, rows, 2 * UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s,
+                                           false, nullptr, 0, UNITS));
+            else RVB_CHECK(gemm::run_tc(XA, p.wa_hiT, p.wa_loT, nullptr, ATT, rows, UNITS, 3 * UNITS, RVB_PREC_FP32, p.abort_flag, s));
             auto fcs = (p.W == 1) ? fc_search_kernel<1> : (p.W <= 5) ? fc_search_kernel<5> : fc_search_kernel<9>;
             fcs<<<ab, 128, 0, s>>>(ATT, p.wfc, p.bfc, lp, fin, len, tok, parent, first_done, p.scores, p.step_ids,
                                    p.parent_ids, p.B, p.W, p.S, t, XA, X, f16 ? x_hi : nullptr, f16 ? x_lo : nullptr,

@@ -56,7 +56,8 @@ bool tc_available();
 int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream_t s);
 int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cudaStream_t s);
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
-               int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false, const CellEpilogue *cell = nullptr);
+               int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false, const CellEpilogue *cell = nullptr,
+               long long lda = 0, int n_out = 0);       // lda: row pitch of the A planes (0 = K); n_out: columns of C (0 = N; W padded beyond it)
 }  // namespace gemm
 
 namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >= 2), decoder_wave.cu
@@ -70,6 +71,8 @@ struct Params {
     const float *wm_hiT, *wm_loT;   // W_mem^T as a [K=128, N=256] weight, transposed [256,128]
     const float *wa_hiT, *wa_loT;   // attention layer [384,128], transposed [128,384]
     const void *wg16_hi, *wg16_lo, *wm16_hi, *wm16_lo;   // fp16 hi / lo planes of the first two (transposed); nullptr: tf32 path
+    const void *wa16_hi, *wa16_lo;  // fp16 hi / lo planes of the attention layer, zero-padded to 256 output columns, transposed [256,384];
+                                    // nullptr: the attention-layer GEMM takes fp32 [h | ctx] rows on the tf32 path
     const float *wtok;          // [7][512] kernel row of token v + bias, [unit][gate] columns
     const void *wg1_16_hi, *wg1_16_lo;   // decoder_depth 2: fp16 hi / lo planes of [kernel ; recurrent kernel] of cell 1, transposed [512,256]
     const float *b1;            // decoder_depth 2: bias of cell 1, [512] in [unit][gate] order
@@ -93,7 +96,8 @@ int run(const Params &p, cudaStream_t stream);
 namespace atc {     // K4 attention on tcgen05, attention_tc.cu: fp16 hi + lo planes (parity mode, widths >= 2), or v_lo == nullptr:
                     // one fp16 plane (reduced-precision mode, every width)
 int run(const uint16_t *v_hi, const uint16_t *v_lo, const uint8_t *mask, const float *Q, float *xa, const int32_t *skip,
-        int B, int Tm, int W, int *abort_flag, cudaStream_t s);
+        int B, int Tm, int W, int *abort_flag, cudaStream_t s, uint16_t *xp_hi = nullptr, uint16_t *xp_lo = nullptr);
+// xp_hi / xp_lo != nullptr: the context goes out as fp16 hi / lo planes at [row*384 + 128 + column] INSTEAD of fp32 into xa
 }  // namespace atc
 
 }  // namespace rvb

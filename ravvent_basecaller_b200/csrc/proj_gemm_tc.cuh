@@ -332,7 +332,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                           const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                           const __grid_constant__ CUtensorMap map_c,
                           const float *__restrict__ bias, long long M, int N, int K, int *abort_flag, float *__restrict__ c_blocked,
-                          const CellEpilogue cell) {
+                          const CellEpilogue cell, int n_out) {
     using cfg = PCfg<NPASS, F16IN, PAIR>;
     constexpr bool MC = PAIR == 1, SM2 = PAIR == 2;
     extern __shared__ unsigned char smem_dyn[];
@@ -545,6 +545,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     if (SM2) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0); }
                     else mbar_arrive(&acc_empty[as]);
                 }
+                if (n_tile * PBN + c0 >= n_out) continue;  // columns beyond the output (a weight padded up to the 256-column tile)
                 if (c_blocked != nullptr) {                // blocked layout: lane = row, 16 bytes per lane, 512 contiguous bytes per warp store
                     float4 *dst = reinterpret_cast<float4 *>(c_blocked) + ((size_t)m_tile * (N >> 2) + ((n_tile * PBN + c0) >> 2)) * BM + row;
 #pragma unroll
@@ -696,7 +697,8 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
 template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
                       long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0, bool blocked_out = false,
-                      const CellEpilogue *cell_epi = nullptr) {
+                      const CellEpilogue *cell_epi = nullptr, int n_out = 0) {
+    if (n_out <= 0) n_out = N;                   // C has n_out <= N columns: W may be zero-padded up to a multiple of the tile
     float *c_blocked = blocked_out ? C : nullptr;
     CellEpilogue cell{};
     if (cell_epi != nullptr) cell = *cell_epi;
@@ -719,7 +721,7 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
     const bool mc = PAIRED != 0 && pair_env != 0 && tiles >= 2LL * sms;
     RVB_CHECK(make_map(&mh, WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
     RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
-    RVB_CHECK(make_map(&mc_map, C, M, N, BM, 32));
+    RVB_CHECK(make_map(&mc_map, C, M, n_out, BM, 32));
     if (mc) {
         auto kern = (pair_env == 1) ? gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED ? 1 : 0> : gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED>;
         const size_t smem_bytes = (pair_env == 1) ? cfg::SMEM : cfgp::SMEM;
@@ -733,12 +735,12 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
         ProfScope ps(KK_GEMM, stream);
-        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell));
+        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell, n_out));
     } else {
         RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
         ProfScope ps(KK_GEMM, stream);
-        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell);
+        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell, n_out);
     }
     RVB_LAUNCH_CHECK();
     count_launch();
