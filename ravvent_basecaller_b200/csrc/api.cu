@@ -453,6 +453,9 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
         const long long nbp = ((long long)nb + 127) / 128 * 128;    // rows per timestep of the fp16 planes and of the blocked G
         rectc::Params p{};
         p.x = x; p.G = G; p.g_bs = 2 * GATES; p.g_ts = nbp * 2 * GATES; p.g_blocked = 1; p.g_rows_per_t = nbp;
+        // reduced precision: the pre-gates cross HBM as fp16 (K2 writes, K3 reads half the bytes of the encoder's largest tensor)
+        const bool g16 = m->precision != RVB_PREC_FP32;
+        p.g16 = (l > 0 && g16) ? 1 : 0;
         p.bimg = m->d_bimg[e][l]; p.w0 = m->d_w0[e];
         p.state_in = l == 0 ? nullptr : m->st[e][(l - 1) & 1];
         p.state_out = m->st[e][l & 1];
@@ -473,7 +476,7 @@ static int encode_branch(rvb_model *m, int e, const float *x, int T, int nb, flo
             const uint16_t *a_hi = reinterpret_cast<const uint16_t *>(yb[(l - 1) & 1]);
             // rows b >= nb of a timestep are padding: never written by K3, projected as they are, never read back
             RVB_CHECK(gemm::run_tc_f16(a_hi, a_hi + (size_t)nbp * T * ENC_OUT, m->d_phi16[e][l], m->d_plo16[e][l], m->d_pb[e][l], G,
-                                       nbp * T, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s, true));
+                                       nbp * T, 2 * GATES, ENC_OUT, m->precision, m->d_abort, s, true, nullptr, 0, 0, g16));
         }
         RVB_CHECK(rectc::run(l == 0 ? feat : 0, p, s));
     }

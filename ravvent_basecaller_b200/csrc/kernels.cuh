@@ -11,6 +11,7 @@ struct Params {
     long long g_bs, g_ts;
     int g_blocked;              // 1: G is [row tile of 128][column quad][128 rows][4] with row = t * g_rows_per_t + b (coalesced by lane)
     long long g_rows_per_t;     // padded batch (multiple of 128) of the blocked layout
+    int g16;                    // 1 (reduced-precision mode only, blocked): the quads are 4 fp16 values (8 bytes), as K2 writes them there
     const uint16_t *bimg;       // [dir][rank] pre-swizzled fp16 hi/lo B-operand images (pack_b_image)
     const float *w0;            // [dir][6][512] layer-0 input rows + bias row, [unit][gate] column order
     const float *state_in;      // [B,2,2,128] or nullptr
@@ -57,7 +58,9 @@ int split_planes_f16(const float *X, void *hi, void *lo, long long n, cudaStream
 int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cudaStream_t s);
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
                int N, int K, int precision, int *abort_flag, cudaStream_t s, bool blocked_out = false, const CellEpilogue *cell = nullptr,
-               long long lda = 0, int n_out = 0);       // lda: row pitch of the A planes (0 = K); n_out: columns of C (0 = N; W padded beyond it)
+               long long lda = 0, int n_out = 0, bool blocked_half = false);
+// lda: row pitch of the A planes (0 = K); n_out: columns of C (0 = N; W padded beyond it); blocked_half: the blocked output holds
+// fp16 quads (8 bytes per row and column quad) instead of fp32 ones
 }  // namespace gemm
 
 namespace decw {    // K4 + K5 per decode step over the whole wave (beam width >= 2), decoder_wave.cu

@@ -18,6 +18,7 @@
 // (see the kernel comment): per step four cluster-scope mbarriers (quarter drained + K-block written ->
 // MMA) and four multicast tcgen05.commit (quarter accumulated -> both CTAs' epilogues).  Waits are bounded.
 #include <cuda_fp16.h>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "cell_math.cuh"
@@ -374,25 +375,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
         // merge the loaded registers right after the load, i.e. wait for it, which defeats the prefetch.
         const long long gq = p.g_blocked ? ROWS : 1;
         const int bg = p.g_blocked ? (b < (int)p.g_rows_per_t ? b : 0) : (live ? b : 0);
-        auto g_at = [&](int tt) -> const float4 * {
-            if (p.g_blocked) {
+        // Reduced-precision mode (NPASS == 1): K2 writes the pre-gates as fp16, 8 bytes per unit in the same blocked order --
+        // half the K2-write / K3-read traffic of the encoder's largest tensor.
+        constexpr bool G16 = PRE && NPASS == 1;
+        using GV = typename std::conditional<G16, uint2, float4>::type;
+        auto g_at = [&](int tt) -> const GV * {
+            if (G16 || p.g_blocked) {
                 const size_t rg = (size_t)tt * p.g_rows_per_t + bg;
-                return reinterpret_cast<const float4 *>(p.G) + ((rg >> 7) * (2 * GATES / 4) + dir * (GATES / 4)) * ROWS + (rg & 127);
+                return reinterpret_cast<const GV *>(p.G) + ((rg >> 7) * (2 * GATES / 4) + dir * (GATES / 4)) * ROWS + (rg & 127);
             }
-            return reinterpret_cast<const float4 *>(p.G + (size_t)bg * p.g_bs + (size_t)tt * p.g_ts + dir * GATES);
+            return reinterpret_cast<const GV *>(p.G + (size_t)bg * p.g_bs + (size_t)tt * p.g_ts + dir * GATES);
+        };
+        auto g_quad = [](const GV &v, float &a, float &b2, float &c2, float &d2) {
+            if constexpr (G16) {
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&v.x)), hi = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+                a = lo.x; b2 = lo.y; c2 = hi.x; d2 = hi.y;
+            } else { a = v.x; b2 = v.y; c2 = v.z; d2 = v.w; }
         };
         // chunk i of a step (i = n*CPQ + ch) -> first unit
         auto unit_of = [&](int i) -> int { return UQ * (i / CPQ) + UPQ * cg + 8 * (i % CPQ); };
         // Software pipeline: the pre-gates of chunks i+1 and i+2 are in flight while chunk i is computed (two register
         // buffers by chunk parity; NCH is even, so the parity carries over the step boundary), and the accumulators of chunk
         // i+1 are loaded from TMEM as soon as those of chunk i have been consumed.
-        float4 gbuf[2][8];
+        GV gbuf[2][8];
         float xnext[F];
         const int bx = live ? b : 0;
         {
             const int t0 = dir ? T - 1 : 0;
             if (PRE) {
-                const float4 *g0 = g_at(t0);
+                const GV *g0 = g_at(t0);
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
 #pragma unroll
@@ -413,8 +424,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
 #pragma unroll
                 for (int f = 0; f < F; ++f) xnext[f] = __ldg(p.x + ((size_t)bx * T + tx) * F + f);
             }
-            const float4 *grow = PRE ? g_at(t) : nullptr;
-            const float4 *grow_next = PRE ? g_at(s + 1 < T ? tn : t) : nullptr;      // last step: harmless reloads of this step's rows
+            const GV *grow = PRE ? g_at(t) : nullptr;
+            const GV *grow_next = PRE ? g_at(s + 1 < T ? tn : t) : nullptr;          // last step: harmless reloads of this step's rows
             float *yrow = (p.y16_hi == nullptr) ? p.y + (size_t)b * p.y_bs + (size_t)t * p.y_ts + dir * UNITS : nullptr;
             uint32_t r[32];
             ok = mbar_wait(&acc_ready[0], s & 1, p.abort_flag);
@@ -430,7 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 float z[32];
                 if (PRE) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) { z[4 * k] = gbuf[i & 1][k].x; z[4 * k + 1] = gbuf[i & 1][k].y; z[4 * k + 2] = gbuf[i & 1][k].z; z[4 * k + 3] = gbuf[i & 1][k].w; }
+                    for (int k = 0; k < 8; ++k) g_quad(gbuf[i & 1][k], z[4 * k], z[4 * k + 1], z[4 * k + 2], z[4 * k + 3]);
                 } else {
                     const uint32_t wr = w0_sh + 16 * u0;
 #pragma unroll
@@ -458,14 +469,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) lstm_rec
                 // at the end of a quarter (MEMBAR.ALL.CTA) waits for this thread's outstanding loads, so the last chunk of a
                 // quarter issues its refill AFTER the fence and the others as early as possible.
                 auto refill = [&]() {
-                    const float4 *nsrc = (i + 2 < NCH) ? grow : grow_next;
+                    const GV *nsrc = (i + 2 < NCH) ? grow : grow_next;
                     const int un = unit_of((i + 2) % NCH);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) gbuf[i & 1][k] = __ldg(nsrc + (size_t)(un + k) * gq);
                     if (PF_CHUNKS > 0) {
                         // registers hold two chunks (64 KB in flight per SM is not enough for the DRAM latency): keep PF_CHUNKS more on
                         // their way into L2.  Measured: 13.2 -> 11.6 us per step; a bulk prefetch of whole steps ADDS DRAM traffic.
-                        const float4 *psrc = (i + 2 + PF_CHUNKS < NCH) ? grow : grow_next;
+                        const GV *psrc = (i + 2 + PF_CHUNKS < NCH) ? grow : grow_next;
                         const int up = unit_of((i + 2 + PF_CHUNKS) % NCH);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(psrc + (size_t)(up + k) * gq));
@@ -564,6 +575,9 @@ static int run_cell(int feat, const Params &p, cudaStream_t stream) {
 
 int run(int feat, const Params &p, cudaStream_t stream) {
     if (p.B <= 0 || p.T <= 0) return RVB_OK;
+    if (feat == 0 && p.precision != RVB_PREC_FP32 && !(p.g16 && p.g_blocked))
+        return fail(RVB_ERR_ARG, "lstm_rec_tc: the reduced-precision pre-gate launch takes blocked fp16 pre-gates (Params::g16)");
+    if (p.g16 && (feat != 0 || p.precision == RVB_PREC_FP32)) return fail(RVB_ERR_ARG, "lstm_rec_tc: fp16 pre-gates only in reduced-precision mode");
     return p.gru ? run_cell<true>(feat, p, stream) : run_cell<false>(feat, p, stream);
 }
 

@@ -169,13 +169,14 @@ int prepare_weights_f16(const float *W, void *hiT, void *loT, int K, int N, cuda
 // the recurrent kernel reads lane-contiguously -- instead of row-major through the staged TMA store.
 int run_tc_f16(const void *Ahi, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C, long long M,
                int N, int K, int precision, int *abort_flag, cudaStream_t stream, bool blocked_out, const CellEpilogue *cell,
-               long long lda, int n_out) {
+               long long lda, int n_out, bool blocked_half) {
     if (M <= 0) return RVB_OK;
+    if (blocked_half && (!blocked_out || precision == RVB_PREC_FP32)) return fail(RVB_ERR_ARG, "gemm_tc_f16: fp16 output only for the blocked layout in reduced-precision mode");
     if (N % 256 != 0 || K % 64 != 0) return fail(RVB_ERR_ARG, "gemm_tc_f16: N %% 256 and K %% 64 must be 0 (N=%d K=%d)", N, K);
     if (blocked_out && M % 128 != 0) return fail(RVB_ERR_ARG, "gemm_tc_f16: blocked output needs M %% 128 == 0 (M=%lld)", M);
     if (cell != nullptr && (N != GATES || precision != RVB_PREC_FP32)) return fail(RVB_ERR_ARG, "gemm_tc_f16: the fused cell epilogue needs N = 512 and the fp32-parity mode");
     if (precision == RVB_PREC_FP32) return tc::launch_persistent<3, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda, blocked_out, cell, n_out);
-    return tc::launch_persistent<1, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda, blocked_out, nullptr, n_out);
+    return tc::launch_persistent<1, true>(Ahi, Alo, WhiT, WloT, bias, C, M, N, K, abort_flag, stream, lda, blocked_out, nullptr, n_out, blocked_half);
 }
 
 }  // namespace gemm

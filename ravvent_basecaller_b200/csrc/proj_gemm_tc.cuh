@@ -331,7 +331,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                           const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                           const __grid_constant__ CUtensorMap map_c,
                           const float *__restrict__ bias, long long M, int N, int K, int *abort_flag, float *__restrict__ c_blocked,
-                          const CellEpilogue cell, int n_out) {
+                          const CellEpilogue cell, int n_out, int blocked_half) {
     using cfg = PCfg<NPASS, F16IN, PAIR>;
     constexpr bool MC = PAIR == 1, SM2 = PAIR == 2;
     extern __shared__ unsigned char smem_dyn[];
@@ -546,7 +546,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 }
                 if (n_tile * PBN + c0 >= n_out) continue;  // columns beyond the output (a weight padded up to the 256-column tile)
                 if (c_blocked != nullptr) {                // blocked layout: lane = row, 16 bytes per lane, 512 contiguous bytes per warp store
-                    float4 *dst = reinterpret_cast<float4 *>(c_blocked) + ((size_t)m_tile * (N >> 2) + ((n_tile * PBN + c0) >> 2)) * BM + row;
+                    const size_t q0i = ((size_t)m_tile * (N >> 2) + ((n_tile * PBN + c0) >> 2)) * BM + row;
+                    float4 *dst = reinterpret_cast<float4 *>(c_blocked) + q0i;
+                    uint2 *dst16 = reinterpret_cast<uint2 *>(c_blocked) + q0i;      // blocked_half: the same order with fp16 quads
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
@@ -554,7 +556,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + (size_t)n_tile * PBN + c0 + 4 * j));
                             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
                         }
-                        dst[(size_t)j * BM] = v;
+                        if (blocked_half) {
+                            const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+                            dst16[(size_t)j * BM] = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                        } else dst[(size_t)j * BM] = v;
                     }
                     continue;
                 }
@@ -703,7 +708,7 @@ int launch(const float *A, const float *WhiT, const float *WloT, const float *bi
 template <int NPASS, bool F16IN>
 int launch_persistent(const void *A, const void *Alo, const void *WhiT, const void *WloT, const float *bias, float *C,
                       long long M, int N, int K, int *abort_flag, cudaStream_t stream, long long lda = 0, bool blocked_out = false,
-                      const CellEpilogue *cell_epi = nullptr, int n_out = 0) {
+                      const CellEpilogue *cell_epi = nullptr, int n_out = 0, bool blocked_half = false) {
     if (n_out <= 0) n_out = N;                   // C has n_out <= N columns: W may be zero-padded up to a multiple of the tile
     float *c_blocked = blocked_out ? C : nullptr;
     CellEpilogue cell{};
@@ -741,12 +746,12 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         lc.attrs = at; lc.numAttrs = 1;
         ProfScope ps(KK_GEMM, stream);
-        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell, n_out));
+        RVB_CUDA(cudaLaunchKernelEx(&lc, kern, ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell, n_out, blocked_half ? 1 : 0));
     } else {
         RVB_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<NPASS, F16IN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM));
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
         ProfScope ps(KK_GEMM, stream);
-        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell, n_out);
+        gemm_tc_persistent_kernel<NPASS, F16IN, 0><<<grid, PTHREADS, cfg::SMEM, stream>>>(ma, mal, mh, ml, mc_map, bias, M, N, K, abort_flag, c_blocked, cell, n_out, blocked_half ? 1 : 0);
     }
     RVB_LAUNCH_CHECK();
     count_launch();
