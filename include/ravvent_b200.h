@@ -46,7 +46,7 @@ extern "C" {
 #define RVB_PREC_FP32      0   /* parity mode: split-precision (3-pass) tensor-core products, fp32-accurate     */
 #define RVB_CELL_LSTM      0   /* rvb_model_set_rnn cell_kind */
 #define RVB_CELL_GRU       1
-#define RVB_PREC_BF16      1   /* reduced mode: single 16-bit pass, fp32 accumulate / cell state, fp16 attention memory */
+#define RVB_PREC_BF16      1   /* reduced mode: single 16-bit pass, fp32 accumulate / cell state, fp16 pre-gates and attention memory */
 
 typedef struct rvb_model rvb_model_t;
 
