@@ -1,9 +1,10 @@
 """Reduced-precision mode (`precision='bf16'`): single-pass 16-bit tensor-core operands in K3 / K2 (fp16 values,
-fp32 accumulate and cell state) and an fp16 copy of the attention memory for the decoder.
+fp32 accumulate and cell state), fp16 pre-gates between K2 and K3, and an fp16 copy of the attention memory for the
+decoder (read by the single-plane tcgen05 attention at every beam width).
 
-Stated tolerances against the fp32 oracle (north_star: "with stated bf16 tolerances"); measured on the first
-run: encoder max |err| 1.1e-4 (rms 2.3e-5), logits 7e-5, cumulative beam scores 4e-4, all search outputs
-identical.  The asserted bounds leave ~10x headroom."""
+Stated tolerances against the fp32 oracle (north_star: "with stated bf16 tolerances"), unchanged since round 1; measured:
+encoder max |err| 1.7e-4 (rms 2.6e-5; 1.1e-4 / 2.3e-5 before the pre-gates went to fp16), logits 7e-5, cumulative beam
+scores 4e-4, all search outputs identical.  The asserted bounds leave ~6x headroom."""
 import numpy as np
 import pytest
 
@@ -38,7 +39,7 @@ def test_encoder_within_stated_tolerance(kind):
     assert err.max() > 1e-6, "suspiciously exact: is the reduced-precision path really selected?"
 
 
-@pytest.mark.parametrize("W", [1, 5])
+@pytest.mark.parametrize("W", [1, 5, 9])       # the three beam buckets of the single-plane attention kernel
 def test_search_within_stated_tolerance(W):
     x = mr.synth_chunks(np.random.default_rng(2), 96)
     bc = make("joint")
