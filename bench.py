@@ -576,7 +576,10 @@ def event_only_bench(args, local_rank, tm, n_reads=96, read_len=60000):
         return bc.beam_search_prediction(ev_all[:n], 1, MAX_OUTPUT_LEN)[0]
 
     k = max(2, args.steps // 2)
-    res = tm.run(pipeline, k, 1, profile=True)
+    # this pipeline is host sensitive (a device-to-host count per read, ~150 us of GPU work per decode step at Tm = 30): the
+    # wall time comes from an unprofiled run, the kernels' share from a second, profiled one
+    res = tm.run(pipeline, k, 1)
+    res["prof"] = tm.run(pipeline, k, 1, profile=True)["prof"]
     n = state["n"]
     return {"config": "BASELINE configs[1]: event-only model fed by GPU event detection, beam 1, S=33", "reads": n_reads,
             "samples": int(n_reads * read_len), "snippets": n, "ms_per_step": res["ms"],
