@@ -541,7 +541,8 @@ def synth_reads(n_reads, read_len, seed=77, distinct=8):
 
 def event_only_bench(args, local_rank, tm, n_reads=96, read_len=60000):
     """BASELINE configs[1] as ONE timed pipeline: raw reads on the device -> K1 event scan (all reads in one launch) ->
-    snippet builder (per read) -> event encoder + attention decoder + beam 1.  96 reads x 60 000 samples ~ 100k snippets."""
+    batched snippet builder (all reads in one call) -> event encoder + attention decoder + beam 1.
+    96 reads x 60 000 samples ~ 100k snippets."""
     import ctypes as C
     import torch
     import ravvent_basecaller_b200 as rb
@@ -553,31 +554,17 @@ def event_only_bench(args, local_rank, tm, n_reads=96, read_len=60000):
     d_sig = torch.from_numpy(sig).to(dev)
     det = rb.EventDetector(6, 9, device=local_rank)
     bc = rb.Basecaller(128, 128, 128, rb.nuc_tk, "event", 0., device=local_rank, precision=args.precision).load_weights(seed=22)
-    cap_total = n_reads * (read_len // 40)
-    ev_all = torch.zeros((cap_total, dl.MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
-    raw_scratch = torch.zeros((read_len // 40, dl.MAX_RAW_LEN, 1), dtype=torch.float32, device=dev)
     state = {}
 
     def pipeline():
-        ev = det.detect_batch(d_sig, offs)
-        counts = ev["count"].cpu().numpy()
-        n = 0
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        for r in range(n_reads):
-            e0 = int(ev["event_offsets"][r])
-            cnt = C.c_int32(0)
-            st, ln, mu, sd = (ev[k][e0:e0 + int(counts[r])] for k in ("start", "length", "mean", "stdv"))
-            cap = max(1, (int(counts[r]) + 5) // 6)
-            _lib.check(_lib.lib.rvb_build_snippets(
-                d_sig[offs[r]:offs[r + 1]].data_ptr(), 4, read_len, st.data_ptr(), ln.data_ptr(), mu.data_ptr(), sd.data_ptr(),
-                int(counts[r]), 0, read_len, 6, raw_scratch.data_ptr(), ev_all[n:].data_ptr(), cap, C.byref(cnt), None, stream))
-            n += cnt.value
-        state["n"] = n
-        return bc.beam_search_prediction(ev_all[:n], 1, MAX_OUTPUT_LEN)[0]
+        # K1 for all reads in one launch, then the batched snippet builder: one device-to-host round trip for the batch
+        _, ev_all, soff = dl.load_data_from_signals(d_sig, offs, stride=6, detector=det, with_raw=False)
+        state["n"] = int(ev_all.shape[0])
+        return bc.beam_search_prediction(ev_all, 1, MAX_OUTPUT_LEN)[0]
 
     k = max(2, args.steps // 2)
-    # this pipeline is host sensitive (a device-to-host count per read, ~150 us of GPU work per decode step at Tm = 30): the
-    # wall time comes from an unprofiled run, the kernels' share from a second, profiled one
+    # this pipeline is host sensitive (~150 us of GPU work per decode step at Tm = 30, against five launches): the wall time
+    # comes from an unprofiled run, the kernels' share from a second, profiled one
     res = tm.run(pipeline, k, 1)
     res["prof"] = tm.run(pipeline, k, 1, profile=True)["prof"]
     n = state["n"]
@@ -585,8 +572,8 @@ def event_only_bench(args, local_rank, tm, n_reads=96, read_len=60000):
             "samples": int(n_reads * read_len), "snippets": n, "ms_per_step": res["ms"],
             "value": n / (res["ms"] * 1e-3) * BASES_PER_CHUNK, "unit": "bases/s", "samples_per_s": n_reads * read_len / (res["ms"] * 1e-3),
             "kernel_ms_per_step": {kk: round(v["ms"] / k, 3) for kk, v in res["prof"].items() if v["ms"] > 0},
-            "note": "wall = event scan (one launch for all reads) + per-read snippet-builder calls (a host sync each: the count comes "
-                    "back to size the next call) + event model; the model itself is the kernel_ms figures"}
+            "note": "wall = event scan (one launch for all reads) + batched snippet builder (one call, one host round trip for the "
+                    "snippet count) + event model; the model itself is the kernel_ms figures"}
 
 
 def kernel_rooflines(prof, steps, chunks, beam, peak_hbm, precision="fp32", valid_rows=float(T_RAW + T_EV)):

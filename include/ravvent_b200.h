@@ -101,6 +101,22 @@ int rvb_build_snippets(const void *d_signal, int sample_bytes, int64_t n_samples
                        float *d_raw_snips, float *d_event_snips, int32_t max_snippets,
                        int32_t *h_n_snippets, int32_t *d_raw_ranges, void *stream);
 
+/* The same for a batch of whole reads (label range = the read, the inference case; the reference loops over reads on the
+ * host, ravvent_performance_evaluator.py:60-66): the arguments are what rvb_event_detect took and left --
+ *   d_signal            all reads concatenated, read r at samples [h_read_offsets[r], h_read_offsets[r+1])
+ *   h_event_offsets     [n_reads+1] capacity offsets of the event arrays, d_counts [n_reads] events detected per read
+ * Snippets of read r follow those of read r-1:
+ *   d_snippet_offsets   optional [n_reads+1] int64 (device): first snippet of each read, total last
+ *   d_raw_snips         [max_snippets,200,1] f32 or NULL (event-only model), d_event_snips [max_snippets,30,5] f32
+ *   d_raw_ranges        optional [max_snippets,2] int32, relative to the snippet's own read; may be NULL
+ *   h_n_snippets        total number of snippets (host): ONE device-to-host copy and stream sync for the whole batch
+ * RVB_ERR_OVERFLOW (nothing beyond the capacity is written) when the batch yields more than max_snippets. */
+int rvb_build_snippets_batch(const void *d_signal, int sample_bytes, const int64_t *h_read_offsets, int32_t n_reads,
+                             const int64_t *h_event_offsets, const int32_t *d_ev_start, const int32_t *d_ev_length,
+                             const double *d_ev_mean, const double *d_ev_stdv, const int32_t *d_counts,
+                             int32_t stride, float *d_raw_snips, float *d_event_snips, int64_t max_snippets,
+                             int64_t *d_snippet_offsets, int32_t *d_raw_ranges, int64_t *h_n_snippets, void *stream);
+
 /* ------------------------------------------------------------------------
  * Model handle -- replaces Basecaller.__init__ / load_weights
  * (basecaller.py:158-206; ravvent_performance_evaluator.py:89-107).

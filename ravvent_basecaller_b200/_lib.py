@@ -39,6 +39,7 @@ _PROTOS = {
     "rvb_event_detect_workspace_bytes": (_i, [_p, C.c_int32, _p]),
     "rvb_event_detect": (_i, [_p, _i, _p, C.c_int32, _i, _i, _d, _d, _d, _p, _p, _p, _p, _p, _p, _p, _sz, _i, _p]),
     "rvb_build_snippets": (_i, [_p, _i, _i64, _p, _p, _p, _p, C.c_int32, _i64, _i64, C.c_int32, _p, _p, C.c_int32, _p, _p, _p]),
+    "rvb_build_snippets_batch": (_i, [_p, _i, _p, C.c_int32, _p, _p, _p, _p, _p, _p, C.c_int32, _p, _p, _i64, _p, _p, _p, _p]),
     "rvb_model_create": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
     "rvb_model_destroy": (_i, [_p]),
     "rvb_model_set_rnn": (_i, [_p, _i, _i]),

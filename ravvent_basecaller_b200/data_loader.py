@@ -104,6 +104,53 @@ def load_data_from_signal(raw, label_start=None, label_end=None, stride=6, devic
     return raw_s[:cnt.value], ev_s[:cnt.value]
 
 
+def load_data_from_signals(signal, read_offsets, stride=6, device=None, detector=None, with_raw=True, return_ranges=False):
+    """``load_data_from_signal`` for a batch of whole reads in ONE pass: one event-detection launch for all reads (K1) and one
+    call of the batched snippet builder (``rvb_build_snippets_batch``) -- a single device-to-host round trip instead of one
+    per read.  The reference loops over the reads of a directory on the host (ravvent_performance_evaluator.py:60-66).
+
+    signal: 1-D integer samples of all reads concatenated (array or device tensor); read_offsets: n_reads + 1.
+    -> (raw_snippets [Ns,200,1] f32 or None if not with_raw, event_snippets [Ns,30,5] f32, snippet_offsets [n_reads+1] int64)
+    on the device; the snippets of read r are rows snippet_offsets[r] .. snippet_offsets[r+1]."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    from .event_detector import EventDetector
+    det = detector or EventDetector(ED_WINDOW_LENGTH_1, ED_WINDOW_LENGTH_2, device=device)
+    dev = det.device
+    offs = np.ascontiguousarray(np.asarray(read_offsets, dtype=np.int64))
+    n_reads = offs.size - 1
+    if isinstance(signal, torch.Tensor):
+        sig = signal.to(dev)
+        if sig.dtype not in (torch.int16, torch.int32):
+            sig = sig.to(torch.int32)
+    else:
+        arr = np.asarray(signal)
+        if arr.dtype != np.int16:
+            arr = arr.astype(np.int32)
+        sig = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    sig = sig.contiguous()
+    ev = det.detect_batch(sig, offs)
+    ev_offs = np.ascontiguousarray(ev["event_offsets"], dtype=np.int64)
+    # capacity: a read of E events has at most ceil(E / stride) windows, and E <= its event capacity
+    cap = int(np.sum((np.diff(ev_offs) + int(stride) - 1) // int(stride))) if n_reads else 0
+    cap = max(cap, 1)
+    with torch.cuda.device(dev):
+        raw_s = torch.zeros((cap, MAX_RAW_LEN, 1), dtype=torch.float32, device=dev) if with_raw else None
+        ev_s = torch.zeros((cap, MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
+        soff = torch.zeros(n_reads + 1, dtype=torch.int64, device=dev)
+        ranges = torch.zeros((cap, 2), dtype=torch.int32, device=dev) if return_ranges else None
+        total = C.c_int64(0)
+        _lib.check(_lib.lib.rvb_build_snippets_batch(
+            sig.data_ptr(), sig.element_size(), offs.ctypes.data, n_reads, ev_offs.ctypes.data,
+            ev["start"].data_ptr(), ev["length"].data_ptr(), ev["mean"].data_ptr(), ev["stdv"].data_ptr(), ev["count"].data_ptr(),
+            int(stride), None if raw_s is None else raw_s.data_ptr(), ev_s.data_ptr(), cap, soff.data_ptr(),
+            None if ranges is None else ranges.data_ptr(), C.byref(total), torch.cuda.current_stream(dev).cuda_stream))
+    n = total.value
+    out = (None if raw_s is None else raw_s[:n], ev_s[:n], soff)
+    return out + (ranges[:n],) if return_ranges else out
+
+
 def _label_tokens(raw_ranges, nuc_raw_ranges, nuc_reference_symbols):
     """Target token rows of the snippets (data_loader.py:53-61, 101-108, 123-124): the labelled bases whose
     sample ranges intersect each snippet's raw range, wrapped in '$' ... '^', tokenised char-level and

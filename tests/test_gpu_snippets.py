@@ -74,3 +74,35 @@ def test_signal_label_files_match_reference_loader(k, tmp_path):
     assert rs.shape == g[f"raw_snips_{k}"].shape and es.shape == g[f"event_snips_{k}"].shape
     assert _ulp_close(rs, g[f"raw_snips_{k}"]) and _ulp_close(es, g[f"event_snips_{k}"])
     assert tk.dtype == np.int64 and np.array_equal(tk, g[f"tokens_{k}"])
+
+
+def test_batched_builder_equals_the_per_read_one():
+    """rvb_build_snippets_batch (one launch set, one host round trip for all reads) against load_data_from_signal per read:
+    bit-identical snippets, ranges and per-read counts -- including a read too short to yield a window and an empty one."""
+    import torch
+    from ravvent_basecaller_b200 import data_loader as dl
+    rng = np.random.default_rng(11)
+    lens = [6000, 0, 300, 12345, 47, 9000]
+    reads = []
+    for n in lens:
+        steps = rng.integers(0, 2, size=n).cumsum() % 7
+        reads.append((500 + 40 * steps + rng.integers(-6, 7, size=n)).astype(np.int32))
+    sig = np.concatenate(reads) if reads else np.zeros(0, np.int32)
+    offs = np.concatenate(([0], np.cumsum(lens))).astype(np.int64)
+    raw_b, ev_b, soff, rng_b = dl.load_data_from_signals(sig, offs, stride=6, return_ranges=True)
+    soff = soff.cpu().numpy()
+    assert soff[0] == 0 and soff[-1] == ev_b.shape[0] == raw_b.shape[0]
+    n_nonempty = 0
+    for r, read in enumerate(reads):
+        if read.size == 0:
+            assert soff[r + 1] == soff[r]
+            continue
+        raw_1, ev_1, rng_1 = dl.load_data_from_signal(read, stride=6, return_ranges=True)
+        assert soff[r + 1] - soff[r] == ev_1.shape[0], (r, soff[r + 1] - soff[r], ev_1.shape[0])
+        sl = slice(int(soff[r]), int(soff[r + 1]))
+        assert torch.equal(ev_b[sl], ev_1) and torch.equal(raw_b[sl], raw_1) and torch.equal(rng_b[sl], rng_1)
+        n_nonempty += ev_1.shape[0] > 0
+    assert n_nonempty >= 3
+    # event-only form: no raw output
+    none_raw, ev_only, soff2 = dl.load_data_from_signals(sig, offs, stride=6, with_raw=False)
+    assert none_raw is None and torch.equal(ev_only, ev_b) and np.array_equal(soff2.cpu().numpy(), soff)
