@@ -106,8 +106,8 @@ def load_data_from_signal(raw, label_start=None, label_end=None, stride=6, devic
 
 def load_data_from_signals(signal, read_offsets, stride=6, device=None, detector=None, with_raw=True, return_ranges=False):
     """``load_data_from_signal`` for a batch of whole reads in ONE pass: one event-detection launch for all reads (K1) and one
-    call of the batched snippet builder (``rvb_build_snippets_batch``) -- a single device-to-host round trip instead of one
-    per read.  The reference loops over the reads of a directory on the host (ravvent_performance_evaluator.py:60-66).
+    call of the batched snippet builder (``rvb_build_snippets_batch``) -- two device-to-host round trips for the batch (the
+    event counts, to size the outputs, and the snippet total) instead of one per read.  The reference loops over the reads of a directory on the host (ravvent_performance_evaluator.py:60-66).
 
     signal: 1-D integer samples of all reads concatenated (array or device tensor); read_offsets: n_reads + 1.
     -> (raw_snippets [Ns,200,1] f32 or None if not with_raw, event_snippets [Ns,30,5] f32, snippet_offsets [n_reads+1] int64)
@@ -132,12 +132,14 @@ def load_data_from_signals(signal, read_offsets, stride=6, device=None, detector
     sig = sig.contiguous()
     ev = det.detect_batch(sig, offs)
     ev_offs = np.ascontiguousarray(ev["event_offsets"], dtype=np.int64)
-    # capacity: a read of E events has at most ceil(E / stride) windows, and E <= its event capacity
-    cap = int(np.sum((np.diff(ev_offs) + int(stride) - 1) // int(stride))) if n_reads else 0
-    cap = max(cap, 1)
+    # capacity: a read of E events has at most ceil(E / stride) windows.  The detected counts come back first (one small
+    # copy: the event arrays' own capacity, samples / 2, would over-allocate the outputs ~5x); every returned row is
+    # written in full by the builder, so the buffers need no clearing.
+    counts = ev["count"].cpu().numpy().astype(np.int64) if n_reads else np.zeros(0, np.int64)
+    cap = max(int(np.sum((counts + int(stride) - 1) // int(stride))), 1)
     with torch.cuda.device(dev):
-        raw_s = torch.zeros((cap, MAX_RAW_LEN, 1), dtype=torch.float32, device=dev) if with_raw else None
-        ev_s = torch.zeros((cap, MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
+        raw_s = torch.empty((cap, MAX_RAW_LEN, 1), dtype=torch.float32, device=dev) if with_raw else None
+        ev_s = torch.empty((cap, MAX_EVENT_LEN, 5), dtype=torch.float32, device=dev)
         soff = torch.zeros(n_reads + 1, dtype=torch.int64, device=dev)
         ranges = torch.zeros((cap, 2), dtype=torch.int32, device=dev) if return_ranges else None
         total = C.c_int64(0)
