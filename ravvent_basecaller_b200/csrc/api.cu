@@ -549,8 +549,11 @@ static int search(rvb_model *m, const float *d_raw, int t_raw, const float *d_ev
         // beam widths >= 2: the attention runs on tcgen05 and reads the memory as fp16 hi / lo planes, which the last encoder
         // layer then writes INSTEAD of the fp32 rows (same bytes)
         // reduced precision: the memory is ONE fp16 plane (K3 writes it next to the fp32 rows), also read on tcgen05, at every width
-        const bool tc16 = m->precision == RVB_PREC_BF16 && m->att16_tc;
-        const bool tc_att = beam && m->att_tc && W >= 2 && !tc16;
+        // Both tcgen05 forms walk a snippet as a chain of tile hand-offs with a floor of ~0.1 ms per launch; the FFMA kernels'
+        // time is proportional to the memory length and wins below ~100 rows (event-only model, Tm = 30: 0.03 vs 0.11 ms).
+        const bool long_memory = Tm >= 128;
+        const bool tc16 = m->precision == RVB_PREC_BF16 && m->att16_tc && long_memory;
+        const bool tc_att = beam && m->att_tc && W >= 2 && !tc16 && long_memory;
         RVB_CHECK(encode_wave(m, need_raw ? d_raw + (size_t)b0 * t_raw : nullptr, t_raw,
                               need_ev ? d_event + (size_t)b0 * t_event * 5 : nullptr, t_event, nb, Tm, s, tc_att));
         // Wave-level decoder: every beam width, decoder depth and cell kind, and greedy search (a mode of its search kernel)
