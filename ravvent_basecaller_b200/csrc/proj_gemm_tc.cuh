@@ -291,6 +291,14 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *map, uint64_t 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
 }
+// cta_group::2 form: executed by both CTAs of the pair, the transaction bytes are credited to the LEADER's copy of the barrier
+// (bit 24 of a shared-memory address selects the odd CTA of a pair; CUTLASS: SM100_TMA_2SM_LOAD_2D), so the MMA issuer
+// waits on one barrier for both halves of a stage and no thread has to relay the peer's arrival.
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
@@ -402,15 +410,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
                     if (round > 0 && !mbar_wait(&empty[s], (uint32_t)((round - 1) & 1), abort_flag)) { ok = false; break; }
-                    mbar_expect_tx(&full[s], cfg::TX_BYTES);
                     const int kc = kb * cfg::K_PER_STAGE;
+                    if (SM2) {
+                        // both CTAs load their own A rows and their half of the W rows (the B operand of the pair's MMA is split
+                        // across the CTAs); every byte is credited to the leader's barrier, which expects both CTAs' stages
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * cfg::TX_BYTES);
+                        const int nrow = n_tile * PBN + (int)rank * (PBN / 2);
+                        tma_load_2d_2sm(&map_a, &full[s], stage_a(s), kc, (int)(m_tile * BM));
+                        if (NPASS == 3 && F16IN) tma_load_2d_2sm(&map_alo, &full[s], stage_a(s) + cfg::A_BYTES, kc, (int)(m_tile * BM));
+                        tma_load_2d_2sm(&map_bhi, &full[s], stage_bhi(s), kc, nrow);
+                        if (NPASS == 3) tma_load_2d_2sm(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kc, nrow);
+                        continue;
+                    }
+                    mbar_expect_tx(&full[s], cfg::TX_BYTES);
                     tma_load_2d(&map_a, &full[s], stage_a(s), kc, (int)(m_tile * BM));
                     if (NPASS == 3 && F16IN) tma_load_2d(&map_alo, &full[s], stage_a(s) + cfg::A_BYTES, kc, (int)(m_tile * BM));
-                    if (SM2) {      // this CTA's half of the W rows: the B operand of the pair's MMA is split across the CTAs
-                        const int nrow = n_tile * PBN + (int)rank * (PBN / 2);
-                        tma_load_2d(&map_bhi, &full[s], stage_bhi(s), kc, nrow);
-                        if (NPASS == 3) tma_load_2d(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES, kc, nrow);
-                    } else if (MC) {   // this CTA's half of the W rows (box = PBN / 2 rows), delivered to both CTAs
+                    if (MC) {   // this CTA's half of the W rows (box = PBN / 2 rows), delivered to both CTAs
                         const int half = (int)rank * (cfg::B_BYTES / 2), nrow = n_tile * PBN + (int)rank * (PBN / 2);
                         tma_load_2d_mc(&map_bhi, &full[s], stage_bhi(s) + half, kc, nrow, (uint16_t)3);
                         if (NPASS == 3) tma_load_2d_mc(&map_blo, &full[s], stage_bhi(s) + cfg::B_BYTES + half, kc, nrow, (uint16_t)3);
@@ -422,15 +437,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             }
         }
     } else if (warp == 1 && SM2 && rank == 1) {
-        if (lane == 0) {                                   // ===== peer CTA: tell the leader when a stage has landed here =====
-            long long g = 0; bool ok = true;
-            for (long long tile = w_first; tile < total && ok; tile += w_step)
-                for (int kb = 0; kb < num_kb; ++kb, ++g) {
-                    const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
-                    if (!mbar_wait(&full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
-                    mbar_arrive_cluster(&peer_full[s], 0);
-                }
-        }
+        // the peer CTA issues no MMAs: the leader's cta_group::2 instructions read both CTAs' stages
     } else if (warp == 1) {
         if (lane == 0) {                                   // ===== MMA issuer =====
             constexpr uint32_t idesc = F16IN ? make_idesc_f16(SM2 ? 2 * BM : BM, PBN) : make_idesc_tf32(BM, PBN);
@@ -443,10 +450,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
                     const int s = (int)(g % cfg::STAGES); const long long round = g / cfg::STAGES;
                     if (!mbar_wait((NPASS == 3 && !F16IN) ? &ready[s] : &full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
-                    if (SM2) {
-                        if (!mbar_wait(&peer_full[s], (uint32_t)(round & 1), abort_flag)) { ok = false; break; }
-                        asm volatile("fence.acq_rel.cluster;" ::: "memory");
-                    }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_bhi(s));
 #pragma unroll
@@ -454,9 +457,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                         const uint32_t koff = ks * 32;
                         const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
                         if (SM2) {
-                            umma_f16_2sm(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
-                            umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
-                            umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+                            if (NPASS == 3) {
+                                umma_f16_2sm(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
+                                umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + cfg::B_BYTES + koff), idesc, 1u);
+                                umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+                            } else {
+                                umma_f16_2sm(d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+                            }
                         } else if (F16IN) {
                             if (NPASS == 3) {
                                 umma_f16(d, make_desc(a_hi + cfg::A_BYTES + koff), make_desc(b_hi + koff), idesc, first);
@@ -545,6 +552,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                     else mbar_arrive(&acc_empty[as]);
                 }
                 if (n_tile * PBN + c0 >= n_out) continue;  // columns beyond the output (a weight padded up to the 256-column tile)
+                if (m_tile >= m_tiles) continue;           // the odd CTA of the last pair when the row tiles do not pair up
                 if (c_blocked != nullptr) {                // blocked layout: lane = row, 16 bytes per lane, 512 contiguous bytes per warp store
                     const size_t q0i = ((size_t)m_tile * (N >> 2) + ((n_tile * PBN + c0) >> 2)) * BM + row;
                     float4 *dst = reinterpret_cast<float4 *>(c_blocked) + q0i;
@@ -713,7 +721,8 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
     float *c_blocked = blocked_out ? C : nullptr;
     CellEpilogue cell{};
     if (cell_epi != nullptr) cell = *cell_epi;
-    constexpr int PAIRED = (F16IN && NPASS == 3) ? 2 : 0;         // cluster form used for the big encoder GEMM
+    // cluster form used for the big encoder GEMM; single-pass (reduced precision): measured 1.28 vs 1.17 ms, not used there
+    constexpr int PAIRED = (F16IN && NPASS == 3) ? 2 : 0;
     using cfg = PCfg<NPASS, F16IN, 0>;
     using cfgp = PCfg<NPASS, F16IN, PAIRED>;
     CUtensorMap ma, mal, mh, ml, mc_map;
@@ -725,17 +734,19 @@ int launch_persistent(const void *A, const void *Alo, const void *WhiT, const vo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long m_tiles = (M + BM - 1) / BM;
     const long long tiles = (long long)(N / PBN) * m_tiles;
-    // cluster-of-two forms of the fp16-plane encoder GEMM (RVB_GEMM_PAIR = 1: W halves multicast, 2: one 2-SM MMA per
-    // pair, 3 stages).  Both are correct and measured but not faster than independent CTAs, the default:
-    // the kernel is bound by its 4:1 write:read HBM stream, not by operand fill or pipeline depth.
-    static const int pair_env = getenv("RVB_GEMM_PAIR") ? atoi(getenv("RVB_GEMM_PAIR")) : 0;
-    const bool mc = PAIRED != 0 && pair_env != 0 && tiles >= 2LL * sms;
+    // Cluster-of-two forms of the fp16-plane GEMM.  2 (the default for the big encoder projection, i.e. the blocked output):
+    // one cta_group::2 MMA per pair -- each SM reads its A rows and HALF of W from shared memory, 8 KB per 64 cycles of
+    // math, where the one-SM M128 N256 K16 MMA needs 12 KB = 96 cycles (tensor pipe <= 67 % busy, measured 62 %).
+    // 1: independent MMAs, W halves TMA-multicast to both CTAs.  RVB_GEMM_PAIR = 0 / 1 / 2 overrides for A/B runs.
+    static const int pair_env = getenv("RVB_GEMM_PAIR") ? atoi(getenv("RVB_GEMM_PAIR")) : -1;
+    const int pair_mode = pair_env >= 0 ? pair_env : (blocked_out ? 2 : 0);
+    const bool mc = PAIRED != 0 && pair_mode != 0 && tiles >= 2LL * sms;
     RVB_CHECK(make_map(&mh, WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
     RVB_CHECK(make_map(&ml, NPASS == 3 ? WloT : WhiT, N, K, mc ? PBN / 2 : PBN, bk, F16IN));
     RVB_CHECK(make_map(&mc_map, C, M, n_out, BM, 32));
     if (mc) {
-        auto kern = (pair_env == 1) ? gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED ? 1 : 0> : gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED>;
-        const size_t smem_bytes = (pair_env == 1) ? cfg::SMEM : cfgp::SMEM;
+        auto kern = (pair_mode == 1) ? gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED ? 1 : 0> : gemm_tc_persistent_kernel<NPASS, F16IN, PAIRED>;
+        const size_t smem_bytes = (pair_mode == 1) ? cfg::SMEM : cfgp::SMEM;
         RVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         const long long pairs = (long long)(N / PBN) * ((m_tiles + 1) / 2);
         const unsigned clusters = (unsigned)(pairs < sms / 2 ? pairs : sms / 2);
