@@ -317,7 +317,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {      // arrive on CTA `rank`'s copy of bar
     uint32_t ra;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(rank));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+    // plain arrive, as K3 does for its `drained` barriers: the .release.cluster form lowers to MEMBAR.ALL.GPU (~1 us per warp and
+    // tile here); the TMEM reads it orders are already complete (tcgen05.wait::ld + tcgen05.fence::before_thread_sync)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_pair() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
